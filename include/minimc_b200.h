@@ -1,0 +1,232 @@
+/* minimc_b200 -- C ABI of the B200-native particle-history transport loop.
+ *
+ * This is the drop-in boundary for the hot path of agtumulak/minimc
+ * (reference @ ed536a2).  The reference has no FFI: its seam is the C++
+ * factory `Driver::Create(path)` + `virtual EstimatorSet Driver::Solve()`
+ * (src/Driver.hpp:23-30), whose fixed-source implementation spawns
+ * `threads` x `std::async(&FixedSource::StartWorker)` (src/FixedSource.cpp:22-36).
+ * Everything below replaces what happens *inside* that Solve(): the host keeps
+ * its World/Material/Nuclide/Estimator objects, flattens them ONCE into the
+ * plain-old-data tables declared here (in the host containers' own iteration
+ * order), and calls these entry points instead of the per-thread history loop.
+ * INTEGRATION.md shows the ~80-line Driver subclass a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function
+ * returns an mmc_status (0 = ok) and never throws; mmc_last_error() gives the
+ * text for the calling thread.  All tables are copied during the call, the
+ * caller keeps ownership of its buffers.  There is NO CPU fallback: without a
+ * CUDA device every compute entry point returns MMC_ERR_NO_DEVICE.
+ */
+#ifndef MINIMC_B200_H
+#define MINIMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMC_ABI_VERSION 1
+
+typedef enum mmc_status {
+  MMC_OK = 0,
+  MMC_ERR_INVALID = 1,      /* malformed table / argument (message says which) */
+  MMC_ERR_NO_DEVICE = 2,    /* no CUDA device: this library has no CPU path */
+  MMC_ERR_CUDA = 3,         /* CUDA runtime error */
+  MMC_ERR_LOST_PARTICLE = 4,/* World::FindCellContaining found no cell (World.cpp:34-36 throws) */
+  MMC_ERR_CAPACITY = 5,     /* per-history secondary queue / pending-score table / trace buffer overflow */
+  MMC_ERR_PHYSICS = 6       /* an assert(false) branch of the reference was reached (e.g. Particle.cpp:123) */
+} mmc_status;
+
+/* CSGSurface.cpp:107-174 */
+typedef enum mmc_surface_type { MMC_SURF_SPHERE = 0, MMC_SURF_PLANEX = 1, MMC_SURF_CYLINDERX = 2 } mmc_surface_type;
+/* TransportMethod.cpp:24-46 */
+typedef enum mmc_tracking { MMC_TRACK_SURFACE = 0, MMC_TRACK_CELL_DELTA = 1 } mmc_tracking;
+/* Particle.hpp:37-45 -- same numbering as Particle::Event */
+typedef enum mmc_event {
+  MMC_EV_BIRTH = 0, MMC_EV_SCATTER = 1, MMC_EV_CAPTURE = 2, MMC_EV_FISSION = 3,
+  MMC_EV_SURFACE_CROSS = 4, MMC_EV_LEAK = 5, MMC_EV_VIRTUAL_COLLISION = 6
+} mmc_event;
+/* RNG stream.  MINSTD_COMPAT reproduces std::minstd_rand consumed through
+ * libstdc++ 13 <random> (BasicTypes.hpp:27) bit for bit; the
+ * counter-based mode is statistically equivalent only. */
+typedef enum mmc_rng_mode { MMC_RNG_MINSTD_COMPAT = 0, MMC_RNG_COUNTER = 1 } mmc_rng_mode;
+/* Source.cpp:44-58 */
+typedef enum mmc_direction_kind { MMC_DIR_CONSTANT = 0, MMC_DIR_ISOTROPIC = 1, MMC_DIR_ISOTROPIC_FLUX = 2 } mmc_direction_kind;
+/* Bins.cpp:19-40 */
+typedef enum mmc_bins_kind { MMC_BINS_NONE = 0, MMC_BINS_LINSPACE = 1, MMC_BINS_LOGSPACE = 2, MMC_BINS_BOUNDARIES = 3 } mmc_bins_kind;
+/* Reaction.hpp:9-13 -- bit positions of mmc_world_desc.mg_reaction_mask */
+enum { MMC_REACTION_CAPTURE = 1, MMC_REACTION_SCATTER = 2, MMC_REACTION_FISSION = 4 };
+/* ScalarField.cpp:35-58 */
+typedef enum mmc_field_kind { MMC_FIELD_CONSTANT = 0, MMC_FIELD_LINEAR = 1 } mmc_field_kind;
+
+/* Flattened `const World` (World.hpp).  Index order is the reference's:
+ * surfaces / nuclides / materials in World creation order (World.cpp:89-168),
+ * cells in XML order (first match wins, World.cpp:26-37), per-cell surfaces and
+ * per-material nuclides in the order the host's std::map iterates them
+ * (Cell.hpp:30, Material.hpp:20 -- pointer-keyed). */
+typedef struct mmc_world_desc {
+  uint32_t struct_size;             /* sizeof(mmc_world_desc) -- ABI check */
+  uint32_t abi_version;             /* MMC_ABI_VERSION */
+
+  int32_t n_surfaces;
+  const int32_t* surface_type;      /* [n_surfaces] mmc_surface_type */
+  const double* surface_param;      /* [n_surfaces][4] sphere: cx cy cz r; planex: c; cylinderx: r */
+
+  int32_t n_cells;
+  const int32_t* cell_material;     /* [n_cells] material index, -1 = void */
+  const int32_t* cell_surface_begin;/* [n_cells+1] CSR offsets */
+  const int32_t* cell_surface_index;/* [nnz] */
+  const int32_t* cell_surface_sense;/* [nnz] 1: cell lies where CSGSurface::Contains() is true ("-1" in XML) */
+  const int32_t* cell_field_kind;   /* [n_cells] mmc_field_kind of the temperature field (Cell.cpp:107-113) */
+  const double* cell_field_param;   /* [n_cells][6] constant: c,-,-,-,upper,lower ; linear: gx,gy,gz,b,upper,lower */
+
+  int32_t n_materials;
+  const double* material_aden;      /* [n_materials] Material::number_density */
+  const int32_t* material_nuclide_begin; /* [n_materials+1] CSR offsets */
+  const int32_t* material_nuclide_index; /* [nnz] */
+  const double* material_nuclide_afrac;  /* [nnz] normalised as Material.cpp:83-92 */
+
+  int32_t n_nuclides;
+  int32_t n_groups;                 /* G >= 1: multigroup world; 0: continuous-energy world */
+
+  /* Multigroup.cpp:23-47,124-186.  All [n_nuclides][G] unless noted; absent
+   * reactions have mask bit 0 and zero rows. */
+  const uint32_t* mg_reaction_mask; /* [n_nuclides] */
+  const double* mg_total;           /* CreateTotalXS: ((0+capture)+scatter)+fission over PRESENT reactions */
+  const double* mg_capture;
+  const double* mg_scatter;         /* column sums of the scatter matrix */
+  const double* mg_fission;
+  const double* mg_nubar;
+  const double* mg_scatter_probs;   /* [n_nuclides][G_in][G_out] NormalizedTwoDimensional */
+  const double* mg_chi;             /* [n_nuclides][G_in][G_out] */
+
+  /* continuous-energy tables: see mmc_ce_desc (NULL for multigroup worlds) */
+  const struct mmc_ce_desc* ce;
+} mmc_world_desc;
+
+/* Source.cpp:131-154: constant position, constant / isotropic / isotropic-flux
+ * direction, constant energy, neutrons. */
+typedef struct mmc_source_desc {
+  double position[3];
+  int32_t direction_kind;           /* mmc_direction_kind */
+  double direction[3];              /* constant direction or isotropic-flux reference; normalised by the callee */
+  uint64_t group;                   /* multigroup worlds: 1..G */
+  double energy;                    /* continuous worlds: MeV */
+} mmc_source_desc;
+
+/* One axis of ParticleBins (Bins.cpp).  n_bins counts the two unbounded end bins. */
+typedef struct mmc_bins_desc {
+  int32_t kind;                     /* mmc_bins_kind */
+  uint64_t n_bins;                  /* NONE: 1; LIN/LOG: bins+2; BOUNDARIES: n_boundaries+1 */
+  double lower, upper, width;       /* LIN: bounds and bin width; LOG: log-space bounds and width */
+  double base;                      /* LOG */
+  const double* boundaries;         /* BOUNDARIES: [n_bins-1] strictly increasing */
+} mmc_bins_desc;
+
+/* CurrentEstimator (Estimator.cpp:116-151) + its ParticleBins (Bins.cpp:174-204). */
+typedef struct mmc_estimator_desc {
+  int32_t surface;                  /* index into mmc_world_desc surfaces */
+  int32_t has_cosine_direction;     /* <cosine u v w> present */
+  double cosine_direction[3];       /* normalised by the callee (Direction ctor) */
+  mmc_bins_desc cosine;
+  mmc_bins_desc energy;
+} mmc_estimator_desc;
+
+/* Device-side bookkeeping; also the inputs of the roofline formula
+ * (BASELINE.md section 4): bytes = 72*births + 144*events + 16*scores + 144*banked. */
+typedef struct mmc_counters {
+  uint64_t n_histories;             /* source particles started */
+  uint64_t n_births;                /* particles started: sources + secondaries */
+  uint64_t n_events;                /* iterations of the Transport loop (= EstimatorSetProxy::Score calls) */
+  uint64_t n_collisions;            /* real collisions (capture+scatter+fission) */
+  uint64_t n_crossings;             /* surface_cross + leak */
+  uint64_t n_virtual;               /* virtual collisions (cell delta tracking) */
+  uint64_t n_scores;                /* non-zero scores accumulated */
+  uint64_t n_secondaries;           /* fission secondaries produced */
+  uint64_t n_banked;                /* sites written to the next-generation bank (k-eigenvalue) */
+  uint64_t n_lost;                  /* particles outside every cell */
+  uint64_t n_capacity_overflow;     /* secondary queue / pending table overflows */
+  uint64_t n_physics_errors;        /* assert(false) branches reached */
+} mmc_counters;
+
+/* One event of one particle, as seen by EstimatorSetProxy::Score (TransportMethod.cpp:74). */
+typedef struct mmc_event_record {
+  uint64_t history;                 /* history index (seed = seed0 + history) */
+  uint32_t particle;                /* ordinal of the particle within its history, reference bank order */
+  int32_t event;                    /* mmc_event; MMC_EV_BIRTH records precede each particle's first event */
+  uint64_t group;                   /* multigroup worlds */
+  double energy;                    /* continuous worlds */
+  int32_t cell;                     /* -1 before the first SetCell */
+  int32_t surface;                  /* Particle::current_surface, -1 if none yet */
+  double position[3];
+  double direction[3];
+  uint64_t rng_state;               /* minstd_rand state after the event */
+} mmc_event_record;
+
+typedef struct mmc_world mmc_world; /* opaque: owns the device copy of the tables */
+
+/* Optional knobs; zero-initialise for defaults. */
+typedef struct mmc_run_options {
+  uint32_t struct_size;             /* sizeof(mmc_run_options) */
+  int32_t device;                   /* CUDA device ordinal; -1 = current */
+  int32_t tracking;                 /* mmc_tracking */
+  int32_t rng_mode;                 /* mmc_rng_mode */
+  uint32_t secondary_capacity;      /* per-history fission queue slots (default 64) */
+  uint32_t pending_capacity;        /* per-history distinct scored bins (default 32) */
+  uint32_t blocks_per_sm;           /* 0 = library default */
+  uint32_t threads_per_block;       /* 0 = library default */
+  void* stream;                     /* cudaStream_t; NULL = the library's own stream */
+} mmc_run_options;
+
+int mmc_abi_version(void);
+/* Copies the message of the calling thread's last failed call into buf. */
+size_t mmc_last_error(char* buf, size_t cap);
+/* Number of visible CUDA devices (0 when there is none / no driver). */
+int mmc_device_count(void);
+
+/* Validates and uploads the tables (replaces nothing in the reference: this is
+ * the one-off flattening of `const World`, World.cpp:20-24). */
+int mmc_world_create(const mmc_world_desc* desc, int device, mmc_world** out);
+void mmc_world_destroy(mmc_world* world);
+
+/* Total number of bins of estimator e = cosine.n_bins * energy.n_bins
+ * (ParticleBins::size, Bins.cpp:192-194). */
+uint64_t mmc_estimator_size(const mmc_estimator_desc* e);
+
+/* Replaces FixedSource::Solve()/StartWorker() (FixedSource.cpp:22-77) for
+ * histories [first_history, first_history + n_histories): history i is sampled
+ * from `std::minstd_rand{seed0 + i}` (FixedSource.cpp:61, Source.cpp:143-154).
+ * scores / square_scores are the concatenation, in estimator order, of
+ * Scorable::scores / square_scores (Scorable.hpp:63-65): they are ADDED to, as
+ * Scorable::operator+= does, so ranks or batches can be chained.  HOST buffers. */
+int mmc_fixed_source_run(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators,
+    int32_t n_estimators, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
+    const mmc_run_options* options, double* scores, double* square_scores, mmc_counters* counters);
+
+/* Same, asynchronous on options->stream, with DEVICE tally buffers of exact
+ * integer counts (the `current` score is 0 or 1 per event, so Sigma s and
+ * Sigma (per-history sum)^2 are integers): d_scores / d_square_scores are
+ * uint64[total bins], d_counters is mmc_counters.  Used by multi-GPU callers that
+ * all-reduce the integers with NCCL before converting to double. */
+int mmc_fixed_source_run_device(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators,
+    int32_t n_estimators, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
+    const mmc_run_options* options, uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters);
+
+/* Parity hook (the reference has none; oracle/ref_harness.cpp obtains the same
+ * records through an extra Estimator): per-event records of histories
+ * [first_history, first_history+n_histories), grouped by history, particles in
+ * the reference's bank order (FixedSource.cpp:63-72).  n_records receives the
+ * number written; MMC_ERR_CAPACITY if cap was too small. */
+int mmc_trace_histories(
+    const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_history,
+    uint64_t n_histories, const mmc_run_options* options, mmc_event_record* records, size_t cap,
+    size_t* n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIMC_B200_H */

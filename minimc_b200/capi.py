@@ -1,0 +1,324 @@
+"""ctypes binding of include/minimc_b200.h (the C ABI of libminimc_b200.so).
+
+Python is plumbing here: the product is the shared library.  Importing this
+module never falls back to a CPU implementation -- if the library is missing,
+`load()` raises, and on a box without a GPU every compute call fails with
+MMC_ERR_NO_DEVICE.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ABI_VERSION = 1
+LIB_PATH = Path(__file__).resolve().parent / "libminimc_b200.so"
+
+# enums of include/minimc_b200.h
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_LOST_PARTICLE, ERR_CAPACITY, ERR_PHYSICS = range(7)
+SURF_SPHERE, SURF_PLANEX, SURF_CYLINDERX = 0, 1, 2
+TRACK_SURFACE, TRACK_CELL_DELTA = 0, 1
+EV_BIRTH, EV_SCATTER, EV_CAPTURE, EV_FISSION, EV_SURFACE_CROSS, EV_LEAK, EV_VIRTUAL_COLLISION = range(7)
+RNG_MINSTD_COMPAT, RNG_COUNTER = 0, 1
+DIR_CONSTANT, DIR_ISOTROPIC, DIR_ISOTROPIC_FLUX = 0, 1, 2
+BINS_NONE, BINS_LINSPACE, BINS_LOGSPACE, BINS_BOUNDARIES = 0, 1, 2, 3
+REACTION_CAPTURE, REACTION_SCATTER, REACTION_FISSION = 1, 2, 4
+FIELD_CONSTANT, FIELD_LINEAR = 0, 1
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+_pu = C.POINTER(C.c_uint32)
+
+
+class WorldDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("abi_version", C.c_uint32),
+        ("n_surfaces", C.c_int32), ("surface_type", _pi), ("surface_param", _pd),
+        ("n_cells", C.c_int32), ("cell_material", _pi), ("cell_surface_begin", _pi),
+        ("cell_surface_index", _pi), ("cell_surface_sense", _pi), ("cell_field_kind", _pi),
+        ("cell_field_param", _pd),
+        ("n_materials", C.c_int32), ("material_aden", _pd), ("material_nuclide_begin", _pi),
+        ("material_nuclide_index", _pi), ("material_nuclide_afrac", _pd),
+        ("n_nuclides", C.c_int32), ("n_groups", C.c_int32),
+        ("mg_reaction_mask", _pu), ("mg_total", _pd), ("mg_capture", _pd), ("mg_scatter", _pd),
+        ("mg_fission", _pd), ("mg_nubar", _pd), ("mg_scatter_probs", _pd), ("mg_chi", _pd),
+        ("ce", C.c_void_p),
+    ]
+
+
+class SourceDesc(C.Structure):
+    _fields_ = [
+        ("position", C.c_double * 3), ("direction_kind", C.c_int32), ("direction", C.c_double * 3),
+        ("group", C.c_uint64), ("energy", C.c_double),
+    ]
+
+
+class BinsDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_bins", C.c_uint64), ("lower", C.c_double), ("upper", C.c_double),
+        ("width", C.c_double), ("base", C.c_double), ("boundaries", _pd),
+    ]
+
+
+class EstimatorDesc(C.Structure):
+    _fields_ = [
+        ("surface", C.c_int32), ("has_cosine_direction", C.c_int32), ("cosine_direction", C.c_double * 3),
+        ("cosine", BinsDesc), ("energy", BinsDesc),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_histories", "n_births", "n_events", "n_collisions", "n_crossings", "n_virtual", "n_scores",
+        "n_secondaries", "n_banked", "n_lost", "n_capacity_overflow", "n_physics_errors")]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class EventRecord(C.Structure):
+    _fields_ = [
+        ("history", C.c_uint64), ("particle", C.c_uint32), ("event", C.c_int32), ("group", C.c_uint64),
+        ("energy", C.c_double), ("cell", C.c_int32), ("surface", C.c_int32), ("position", C.c_double * 3),
+        ("direction", C.c_double * 3), ("rng_state", C.c_uint64),
+    ]
+
+
+class RunOptions(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("tracking", C.c_int32), ("rng_mode", C.c_int32),
+        ("secondary_capacity", C.c_uint32), ("pending_capacity", C.c_uint32), ("blocks_per_sm", C.c_uint32),
+        ("threads_per_block", C.c_uint32), ("stream", C.c_void_p),
+    ]
+
+
+# every symbol include/minimc_b200.h declares
+EXPORTS = (
+    "mmc_abi_version", "mmc_last_error", "mmc_device_count", "mmc_world_create", "mmc_world_destroy",
+    "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_device", "mmc_trace_histories",
+)
+
+_lib = None
+
+
+class MinimcError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"minimc_b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+def load() -> C.CDLL:
+    """Loads libminimc_b200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(minimc_b200 has no CPU or pure-Python transport path)")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib.mmc_abi_version.restype = C.c_int
+    lib.mmc_last_error.restype = C.c_size_t
+    lib.mmc_last_error.argtypes = [C.c_char_p, C.c_size_t]
+    lib.mmc_device_count.restype = C.c_int
+    lib.mmc_world_create.restype = C.c_int
+    lib.mmc_world_create.argtypes = [C.POINTER(WorldDesc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.mmc_world_destroy.restype = None
+    lib.mmc_world_destroy.argtypes = [C.c_void_p]
+    lib.mmc_estimator_size.restype = C.c_uint64
+    lib.mmc_estimator_size.argtypes = [C.POINTER(EstimatorDesc)]
+    run_args = [C.c_void_p, C.POINTER(SourceDesc), C.POINTER(EstimatorDesc), C.c_int32, C.c_uint64, C.c_uint64,
+                C.c_uint64, C.POINTER(RunOptions)]
+    lib.mmc_fixed_source_run.restype = C.c_int
+    lib.mmc_fixed_source_run.argtypes = run_args + [_pd, _pd, C.POINTER(Counters)]
+    lib.mmc_fixed_source_run_device.restype = C.c_int
+    lib.mmc_fixed_source_run_device.argtypes = run_args + [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mmc_trace_histories.restype = C.c_int
+    lib.mmc_trace_histories.argtypes = [
+        C.c_void_p, C.POINTER(SourceDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(RunOptions),
+        C.POINTER(EventRecord), C.c_size_t, C.POINTER(C.c_size_t)]
+    if lib.mmc_abi_version() != ABI_VERSION:
+        raise ImportError(f"ABI mismatch: library {lib.mmc_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(1024)
+    load().mmc_last_error(buf, len(buf))
+    return buf.value.decode()
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise MinimcError(status, last_error())
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class FlatWorld:
+    """The flat tables of mmc_world_desc as numpy arrays (see the header for the
+    meaning and order of every array).  Built by the host flattener
+    (minimc_b200.host) or, in tests, by oracle/flatten.py."""
+
+    FIELDS = {
+        "surface_type": np.int32, "surface_param": np.float64, "cell_material": np.int32,
+        "cell_surface_begin": np.int32, "cell_surface_index": np.int32, "cell_surface_sense": np.int32,
+        "cell_field_kind": np.int32, "cell_field_param": np.float64, "material_aden": np.float64,
+        "material_nuclide_begin": np.int32, "material_nuclide_index": np.int32,
+        "material_nuclide_afrac": np.float64, "mg_reaction_mask": np.uint32, "mg_total": np.float64,
+        "mg_capture": np.float64, "mg_scatter": np.float64, "mg_fission": np.float64, "mg_nubar": np.float64,
+        "mg_scatter_probs": np.float64, "mg_chi": np.float64,
+    }
+
+    def __init__(self, n_groups: int, **arrays):
+        self.n_groups = int(n_groups)
+        for name, dtype in self.FIELDS.items():
+            setattr(self, name, _arr(arrays[name], dtype).reshape(-1))
+        self.n_surfaces = len(self.surface_type)
+        self.n_cells = len(self.cell_material)
+        self.n_materials = len(self.material_aden)
+        self.n_nuclides = len(self.mg_reaction_mask)
+
+    def desc(self) -> WorldDesc:
+        d = WorldDesc()
+        d.struct_size = C.sizeof(WorldDesc)
+        d.abi_version = ABI_VERSION
+        d.n_surfaces, d.n_cells = self.n_surfaces, self.n_cells
+        d.n_materials, d.n_nuclides, d.n_groups = self.n_materials, self.n_nuclides, self.n_groups
+        for name, dtype in self.FIELDS.items():
+            ctype = {np.int32: C.c_int32, np.uint32: C.c_uint32, np.float64: C.c_double}[dtype]
+            setattr(d, name, _ptr(getattr(self, name), ctype))
+        d.ce = None
+        return d
+
+
+def source_desc(position=(0.0, 0.0, 0.0), direction_kind=DIR_ISOTROPIC, direction=(1.0, 0.0, 0.0), group=1,
+                energy=0.0) -> SourceDesc:
+    s = SourceDesc()
+    s.position = (C.c_double * 3)(*position)
+    s.direction_kind = direction_kind
+    s.direction = (C.c_double * 3)(*direction)
+    s.group = group
+    s.energy = energy
+    return s
+
+
+def bins_desc(kind=BINS_NONE, *, bins=0, lower=0.0, upper=0.0, base=10.0, boundaries=None):
+    """Mirrors the constructors of Bins.cpp:57-70,96-110,139-154.  Returns the
+    descriptor and the numpy array that must outlive it."""
+    b = BinsDesc()
+    b.kind = kind
+    keep = None
+    if kind == BINS_NONE:
+        b.n_bins = 1
+    elif kind in (BINS_LINSPACE, BINS_LOGSPACE):
+        b.n_bins = bins + 2
+        b.lower, b.upper, b.base = lower, upper, base
+        b.width = (upper - lower) / bins  # (upper_bound - lower_bound) / (n_bins - 2)
+    elif kind == BINS_BOUNDARIES:
+        keep = _arr(boundaries, np.float64)
+        b.n_bins = len(keep) + 1
+        b.boundaries = _ptr(keep, C.c_double)
+    else:
+        raise ValueError(kind)
+    return b, keep
+
+
+class Estimators:
+    """An array of mmc_estimator_desc plus the buffers it points into."""
+
+    def __init__(self, specs):
+        # specs: list of dicts {surface, cosine_direction|None, cosine: (kind, kwargs), energy: (kind, kwargs)}
+        self._keep = []
+        self.array = (EstimatorDesc * max(len(specs), 1))()
+        self.n = len(specs)
+        self.sizes = []
+        for i, s in enumerate(specs):
+            e = self.array[i]
+            e.surface = s["surface"]
+            cd = s.get("cosine_direction")
+            e.has_cosine_direction = 1 if cd is not None else 0
+            if cd is not None:
+                e.cosine_direction = (C.c_double * 3)(*cd)
+            ck, ckw = s.get("cosine", (BINS_NONE, {}))
+            ek, ekw = s.get("energy", (BINS_NONE, {}))
+            e.cosine, k1 = bins_desc(ck, **ckw)
+            e.energy, k2 = bins_desc(ek, **ekw)
+            self._keep += [k1, k2]
+            self.sizes.append(int(e.cosine.n_bins * e.energy.n_bins))
+        self.total_bins = sum(self.sizes)
+
+
+class World:
+    """Owns an mmc_world handle (the device copy of the tables)."""
+
+    def __init__(self, flat: FlatWorld, device: int = -1):
+        self.flat = flat
+        self._handle = C.c_void_p()
+        desc = flat.desc()
+        check(load().mmc_world_create(C.byref(desc), device, C.byref(self._handle)))
+
+    def close(self):
+        if self._handle:
+            load().mmc_world_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream):
+        o = RunOptions()
+        o.struct_size = C.sizeof(RunOptions)
+        o.device = -1
+        o.tracking = tracking
+        o.rng_mode = RNG_MINSTD_COMPAT
+        o.secondary_capacity = secondary_capacity
+        o.pending_capacity = pending_capacity
+        o.blocks_per_sm = blocks_per_sm
+        o.stream = stream
+        return o
+
+    def fixed_source_run(self, source: SourceDesc, estimators: Estimators, seed0: int, first_history: int,
+                         n_histories: int, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0,
+                         blocks_per_sm=0, scores=None, square_scores=None):
+        """mmc_fixed_source_run with host buffers.  Returns (scores, square_scores, counters dict)."""
+        nb = max(estimators.total_bins, 1)
+        scores = np.zeros(nb) if scores is None else scores
+        square_scores = np.zeros(nb) if square_scores is None else square_scores
+        counters = Counters()
+        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, None)
+        check(load().mmc_fixed_source_run(
+            self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
+            C.byref(o), _ptr(scores, C.c_double), _ptr(square_scores, C.c_double), C.byref(counters)))
+        return scores[:estimators.total_bins], square_scores[:estimators.total_bins], counters.as_dict()
+
+    def fixed_source_run_device(self, source, estimators, seed0, first_history, n_histories, d_scores, d_square,
+                                d_counters, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0,
+                                blocks_per_sm=0, stream=None):
+        """mmc_fixed_source_run_device: raw device pointers (ints), asynchronous on `stream`."""
+        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream)
+        check(load().mmc_fixed_source_run_device(
+            self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
+            C.byref(o), d_scores, d_square, d_counters))
+
+    def trace(self, source, seed0, first_history, n_histories, *, tracking=TRACK_SURFACE, cap=1 << 16):
+        records = (EventRecord * cap)()
+        n = C.c_size_t()
+        o = self._options(tracking, 0, 0, 0, None)
+        check(load().mmc_trace_histories(
+            self._handle, C.byref(source), seed0, first_history, n_histories, C.byref(o), records, cap, C.byref(n)))
+        return [records[i] for i in range(n.value)]

@@ -1,0 +1,520 @@
+// C ABI of include/minimc_b200.h: table validation, flattening into the device
+// blob, scratch management and kernel launches.  No CPU transport path exists
+// in this library: without a CUDA device every compute entry point fails with
+// MMC_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/minimc_b200.h"
+#include "kernels.h"
+#include "world_blob.h"
+
+using namespace mmc;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return status;
+}
+
+#define MMC_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    const cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) return fail(MMC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+// Builds the blob: appends arrays at 16-byte aligned offsets.
+class BlobBuilder {
+public:
+  BlobBuilder() { bytes.resize(sizeof(WorldHeader)); pad(); }
+  template <typename T> uint32_t add(const T* src, size_t n) {
+    pad();
+    const uint32_t off = static_cast<uint32_t>(bytes.size());
+    if (n) {
+      bytes.resize(bytes.size() + n * sizeof(T));
+      std::memcpy(bytes.data() + off, src, n * sizeof(T));
+    }
+    return off;
+  }
+  WorldHeader& header() { return *reinterpret_cast<WorldHeader*>(bytes.data()); }
+  void pad() { bytes.resize((bytes.size() + 15) & ~size_t{15}); }
+  std::vector<char> bytes;
+};
+
+}  // namespace
+
+struct mmc_world {
+  int device = 0;
+  char* d_blob = nullptr;
+  uint32_t blob_bytes = 0;
+  WorldHeader header{};
+  bool has_fission = false;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  // scratch reused between runs
+  BankSite* d_sites = nullptr;
+  size_t sites_bytes = 0;
+  uint2* d_pending = nullptr;
+  size_t pending_bytes = 0;
+  double* d_bounds = nullptr;
+  size_t bounds_bytes = 0;
+  unsigned long long* d_next = nullptr;
+};
+
+namespace {
+
+int validate_world(const mmc_world_desc* d) {
+  if (!d) return fail(MMC_ERR_INVALID, "world desc is NULL");
+  if (d->struct_size != sizeof(mmc_world_desc) || d->abi_version != MMC_ABI_VERSION)
+    return fail(MMC_ERR_INVALID, "mmc_world_desc ABI mismatch: struct_size %u (expected %zu), abi_version %u (expected %d)",
+                d->struct_size, sizeof(mmc_world_desc), d->abi_version, MMC_ABI_VERSION);
+  if (d->n_surfaces < 1 || d->n_cells < 1) return fail(MMC_ERR_INVALID, "world needs at least one surface and one cell");
+  if (d->n_groups < 1) return fail(MMC_ERR_INVALID, "continuous-energy worlds are not supported by this build (n_groups = %d)", d->n_groups);
+  if (d->n_materials < 0 || d->n_nuclides < 0) return fail(MMC_ERR_INVALID, "negative table size");
+  if (!d->surface_type || !d->surface_param || !d->cell_material || !d->cell_surface_begin || !d->cell_surface_index ||
+      !d->cell_surface_sense)
+    return fail(MMC_ERR_INVALID, "geometry table pointer is NULL");
+  for (int i = 0; i < d->n_surfaces; i++)
+    if (d->surface_type[i] < MMC_SURF_SPHERE || d->surface_type[i] > MMC_SURF_CYLINDERX)
+      return fail(MMC_ERR_INVALID, "surface %d: unknown type %d", i, d->surface_type[i]);
+  if (d->cell_surface_begin[0] != 0) return fail(MMC_ERR_INVALID, "cell_surface_begin[0] must be 0");
+  for (int c = 0; c < d->n_cells; c++) {
+    if (d->cell_surface_begin[c + 1] <= d->cell_surface_begin[c])
+      return fail(MMC_ERR_INVALID, "cell %d has no surfaces (Cell::NearestSurface would throw, Cell.cpp:44-47)", c);
+    if (d->cell_material[c] < -1 || d->cell_material[c] >= d->n_materials)
+      return fail(MMC_ERR_INVALID, "cell %d: material index %d out of range", c, d->cell_material[c]);
+    for (int k = d->cell_surface_begin[c]; k < d->cell_surface_begin[c + 1]; k++)
+      if (d->cell_surface_index[k] < 0 || d->cell_surface_index[k] >= d->n_surfaces)
+        return fail(MMC_ERR_INVALID, "cell %d: surface index %d out of range", c, d->cell_surface_index[k]);
+  }
+  if (d->n_materials > 0) {
+    if (!d->material_aden || !d->material_nuclide_begin || !d->material_nuclide_index || !d->material_nuclide_afrac)
+      return fail(MMC_ERR_INVALID, "material table pointer is NULL");
+    if (d->material_nuclide_begin[0] != 0) return fail(MMC_ERR_INVALID, "material_nuclide_begin[0] must be 0");
+    for (int m = 0; m < d->n_materials; m++) {
+      if (d->material_nuclide_begin[m + 1] < d->material_nuclide_begin[m])
+        return fail(MMC_ERR_INVALID, "material %d: decreasing CSR offsets", m);
+      for (int k = d->material_nuclide_begin[m]; k < d->material_nuclide_begin[m + 1]; k++)
+        if (d->material_nuclide_index[k] < 0 || d->material_nuclide_index[k] >= d->n_nuclides)
+          return fail(MMC_ERR_INVALID, "material %d: nuclide index %d out of range", m, d->material_nuclide_index[k]);
+    }
+  }
+  if (d->n_nuclides > 0 &&
+      (!d->mg_reaction_mask || !d->mg_total || !d->mg_capture || !d->mg_scatter || !d->mg_fission || !d->mg_nubar ||
+       !d->mg_scatter_probs || !d->mg_chi))
+    return fail(MMC_ERR_INVALID, "multigroup table pointer is NULL");
+  return MMC_OK;
+}
+
+int ensure_scratch(mmc_world* w, size_t threads, uint32_t sec_cap, uint32_t pend_cap, size_t bounds_count) {
+  const size_t need_sites = threads * sec_cap * sizeof(BankSite);
+  if (need_sites > w->sites_bytes) {
+    if (w->d_sites) cudaFree(w->d_sites);
+    w->d_sites = nullptr;
+    w->sites_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_sites, need_sites));
+    w->sites_bytes = need_sites;
+  }
+  const size_t need_pending = threads * pend_cap * sizeof(uint2);
+  if (need_pending > w->pending_bytes) {
+    if (w->d_pending) cudaFree(w->d_pending);
+    w->d_pending = nullptr;
+    w->pending_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_pending, need_pending));
+    w->pending_bytes = need_pending;
+  }
+  const size_t need_bounds = std::max<size_t>(bounds_count, 1) * sizeof(double);
+  if (need_bounds > w->bounds_bytes) {
+    if (w->d_bounds) cudaFree(w->d_bounds);
+    w->d_bounds = nullptr;
+    w->bounds_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_bounds, need_bounds));
+    w->bounds_bytes = need_bounds;
+  }
+  return MMC_OK;
+}
+
+// Direction ctor: Point{x,y,z} then Normalize() (Point.cpp:80-83, 44-47)
+void normalise(const double in[3], double out[3]) {
+  const double n = std::sqrt(in[0] * in[0] + in[1] * in[1] + in[2] * in[2]);
+  out[0] = in[0] / n;
+  out[1] = in[1] / n;
+  out[2] = in[2] / n;
+}
+
+int fill_bins(const mmc_bins_desc& in, BinsSpec& out, std::vector<double>& bounds, const char* what, int e) {
+  out = BinsSpec{};
+  out.kind = in.kind;
+  switch (in.kind) {
+  case MMC_BINS_NONE:
+    out.n_bins = 1;
+    break;
+  case MMC_BINS_LINSPACE:
+  case MMC_BINS_LOGSPACE:
+    if (in.n_bins < 3) return fail(MMC_ERR_INVALID, "estimator %d %s: n_bins must be bins+2 >= 3", e, what);
+    if (!(in.upper > in.lower)) return fail(MMC_ERR_INVALID, "estimator %d %s: max must be strictly greater than min", e, what);
+    out.n_bins = static_cast<uint32_t>(in.n_bins);
+    out.lower = in.lower;
+    out.upper = in.upper;
+    out.width = in.width;
+    out.base = in.base;
+    break;
+  case MMC_BINS_BOUNDARIES:
+    if (in.n_bins < 1 || (in.n_bins > 1 && !in.boundaries))
+      return fail(MMC_ERR_INVALID, "estimator %d %s: boundaries missing", e, what);
+    for (uint64_t i = 1; i + 1 < in.n_bins; i++)
+      if (!(in.boundaries[i] > in.boundaries[i - 1]))
+        return fail(MMC_ERR_INVALID, "estimator %d %s: nonincreasing elements found", e, what);
+    out.n_bins = static_cast<uint32_t>(in.n_bins);
+    out.off_boundaries = static_cast<uint32_t>(bounds.size());
+    bounds.insert(bounds.end(), in.boundaries, in.boundaries + (in.n_bins - 1));
+    break;
+  default:
+    return fail(MMC_ERR_INVALID, "estimator %d %s: unknown bins kind %d", e, what, in.kind);
+  }
+  return MMC_OK;
+}
+
+struct Prepared {
+  RunSpec run{};
+  std::vector<double> bounds;
+  LaunchConfig cfg{};
+  cudaStream_t stream = nullptr;
+};
+
+int prepare_run(
+    mmc_world* w, const mmc_source_desc* source, const mmc_estimator_desc* estimators, int32_t n_estimators,
+    uint64_t seed0, uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, bool trace,
+    Prepared& out) {
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  if (!source) return fail(MMC_ERR_INVALID, "source desc is NULL");
+  if (n_estimators < 0 || n_estimators > kMaxEstimators)
+    return fail(MMC_ERR_INVALID, "n_estimators %d out of range [0, %d]", n_estimators, kMaxEstimators);
+  if (n_estimators > 0 && !estimators) return fail(MMC_ERR_INVALID, "estimators is NULL");
+  mmc_run_options opt{};
+  if (options) {
+    if (options->struct_size != sizeof(mmc_run_options))
+      return fail(MMC_ERR_INVALID, "mmc_run_options ABI mismatch: struct_size %u (expected %zu)", options->struct_size,
+                  sizeof(mmc_run_options));
+    opt = *options;
+  }
+  if (opt.tracking != MMC_TRACK_SURFACE && opt.tracking != MMC_TRACK_CELL_DELTA)
+    return fail(MMC_ERR_INVALID, "unknown tracking %d", opt.tracking);
+  if (opt.rng_mode != MMC_RNG_MINSTD_COMPAT)
+    return fail(MMC_ERR_INVALID, "rng_mode %d is not available in this build", opt.rng_mode);
+  RunSpec& run = out.run;
+  // source
+  for (int i = 0; i < 3; i++) run.source.position[i] = source->position[i];
+  run.source.direction_kind = source->direction_kind;
+  if (source->direction_kind == MMC_DIR_CONSTANT || source->direction_kind == MMC_DIR_ISOTROPIC_FLUX) {
+    normalise(source->direction, run.source.direction);
+  } else if (source->direction_kind != MMC_DIR_ISOTROPIC) {
+    return fail(MMC_ERR_INVALID, "unknown source direction kind %d", source->direction_kind);
+  }
+  if (source->group < 1 || source->group > static_cast<uint64_t>(w->header.n_groups))
+    return fail(MMC_ERR_INVALID, "source group %llu outside 1..%d", static_cast<unsigned long long>(source->group),
+                w->header.n_groups);
+  run.source.group = source->group;
+  run.source.energy = source->energy;
+  // estimators
+  uint64_t offset = 0;
+  for (int e = 0; e < n_estimators; e++) {
+    const mmc_estimator_desc& in = estimators[e];
+    EstimatorSpec& es = run.estimators[e];
+    if (in.surface < 0 || in.surface >= w->header.n_surfaces)
+      return fail(MMC_ERR_INVALID, "estimator %d: surface index %d out of range", e, in.surface);
+    es.surface = in.surface;
+    es.has_direction = in.has_cosine_direction ? 1 : 0;
+    if (es.has_direction) normalise(in.cosine_direction, es.direction);
+    if (int s = fill_bins(in.cosine, es.cosine, out.bounds, "cosine", e)) return s;
+    if (int s = fill_bins(in.energy, es.energy, out.bounds, "energy", e)) return s;
+    es.stride = es.energy.n_bins;
+    es.offset = offset;
+    offset += static_cast<uint64_t>(es.cosine.n_bins) * es.energy.n_bins;
+  }
+  if (offset > 0xffffffffull) return fail(MMC_ERR_INVALID, "more than 2^32 tally bins");
+  run.n_estimators = n_estimators;
+  run.total_bins = offset;
+  run.tracking = opt.tracking;
+  run.seed0 = seed0;
+  run.first_history = first_history;
+  run.n_histories = n_histories;
+  // capacities
+  uint32_t sec = opt.secondary_capacity ? opt.secondary_capacity : 32;
+  if (!w->has_fission) sec = 1;
+  uint32_t pow2 = 1;
+  while (pow2 < sec) pow2 <<= 1;
+  run.secondary_capacity = pow2;
+  run.pending_capacity = opt.pending_capacity ? opt.pending_capacity : 32;
+  if (n_estimators == 0) run.pending_capacity = 1;
+  run.world_bytes = w->blob_bytes;
+  run.world_in_smem = (!trace && w->blob_bytes <= 96 * 1024) ? 1 : 0;
+  // launch shape
+  int per_sm = max_blocks_per_sm(run.tracking, run.world_in_smem ? run.world_bytes : 0);
+  if (per_sm < 1) per_sm = 1;
+  if (opt.blocks_per_sm && static_cast<int>(opt.blocks_per_sm) < per_sm) per_sm = opt.blocks_per_sm;
+  long long blocks = static_cast<long long>(w->sm_count) * per_sm;
+  const long long useful = static_cast<long long>((n_histories + kThreadsPerBlock - 1) / kThreadsPerBlock);
+  if (blocks > useful) blocks = std::max<long long>(useful, 1);
+  out.cfg.blocks = static_cast<int>(blocks);
+  const uint64_t warps = static_cast<uint64_t>(blocks) * (kThreadsPerBlock / 32);
+  uint64_t chunk = n_histories / (warps * 16);
+  chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 32), 2048);
+  run.chunk = static_cast<uint32_t>(chunk);
+  out.stream = opt.stream ? static_cast<cudaStream_t>(opt.stream) : w->stream;
+  return MMC_OK;
+}
+
+int status_from_counters(const mmc_counters& c) {
+  if (c.n_lost)
+    return fail(MMC_ERR_LOST_PARTICLE,
+                "%llu particle(s) do not belong to any Cell. Please check that all space is either assigned a material or void.",
+                static_cast<unsigned long long>(c.n_lost));
+  if (c.n_physics_errors)
+    return fail(MMC_ERR_PHYSICS, "%llu event(s) reached a branch the reference asserts unreachable",
+                static_cast<unsigned long long>(c.n_physics_errors));
+  if (c.n_capacity_overflow)
+    return fail(MMC_ERR_CAPACITY,
+                "%llu per-history capacity overflow(s): raise secondary_capacity / pending_capacity in mmc_run_options",
+                static_cast<unsigned long long>(c.n_capacity_overflow));
+  return MMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmc_abi_version(void) { return MMC_ABI_VERSION; }
+
+size_t mmc_last_error(char* buf, size_t cap) {
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, g_error.size());
+    std::memcpy(buf, g_error.data(), n);
+    buf[n] = 0;
+  }
+  return g_error.size();
+}
+
+int mmc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
+  if (!e) return 0;
+  auto n = [](const mmc_bins_desc& b) -> uint64_t { return b.kind == MMC_BINS_NONE ? 1 : b.n_bins; };
+  return n(e->cosine) * n(e->energy);
+}
+
+int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
+  if (!out) return fail(MMC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int s = validate_world(d)) return s;
+  if (mmc_device_count() < 1)
+    return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible: minimc_b200 has no CPU transport path");
+  if (device < 0) MMC_CUDA(cudaGetDevice(&device));
+  MMC_CUDA(cudaSetDevice(device));
+
+  const int G = d->n_groups;
+  const int nnz_cell = d->cell_surface_begin[d->n_cells];
+  const int nnz_mat = d->n_materials ? d->material_nuclide_begin[d->n_materials] : 0;
+  BlobBuilder b;
+  std::vector<int32_t> packed(nnz_cell);
+  for (int k = 0; k < nnz_cell; k++) packed[k] = (d->cell_surface_index[k] << 1) | (d->cell_surface_sense[k] ? 1 : 0);
+  std::vector<int32_t> field_kind(d->n_cells, MMC_FIELD_CONSTANT);
+  std::vector<double> field_param(static_cast<size_t>(d->n_cells) * 6, 0.0);
+  if (d->cell_field_kind && d->cell_field_param) {
+    std::copy(d->cell_field_kind, d->cell_field_kind + d->n_cells, field_kind.begin());
+    std::copy(d->cell_field_param, d->cell_field_param + static_cast<size_t>(d->n_cells) * 6, field_param.begin());
+  }
+  WorldHeader h{};
+  h.n_surfaces = d->n_surfaces;
+  h.n_cells = d->n_cells;
+  h.n_materials = d->n_materials;
+  h.n_nuclides = d->n_nuclides;
+  h.n_groups = G;
+  h.off_surface_type = b.add(d->surface_type, d->n_surfaces);
+  h.off_surface_param = b.add(d->surface_param, static_cast<size_t>(d->n_surfaces) * 4);
+  h.off_cell_material = b.add(d->cell_material, d->n_cells);
+  h.off_cell_surf_begin = b.add(d->cell_surface_begin, d->n_cells + 1);
+  h.off_cell_surf = b.add(packed.data(), packed.size());
+  h.off_cell_field_kind = b.add(field_kind.data(), field_kind.size());
+  h.off_cell_field_param = b.add(field_param.data(), field_param.size());
+  const int32_t zero_begin[1] = {0};
+  h.off_mat_aden = b.add(d->material_aden, d->n_materials);
+  h.off_mat_nuc_begin = d->n_materials ? b.add(d->material_nuclide_begin, d->n_materials + 1) : b.add(zero_begin, 1);
+  h.off_mat_nuc_index = b.add(d->material_nuclide_index, nnz_mat);
+  h.off_mat_nuc_afrac = b.add(d->material_nuclide_afrac, nnz_mat);
+  const size_t ng = static_cast<size_t>(d->n_nuclides) * G;
+  h.off_mg_mask = b.add(d->mg_reaction_mask, d->n_nuclides);
+  h.off_mg_total = b.add(d->mg_total, ng);
+  h.off_mg_capture = b.add(d->mg_capture, ng);
+  h.off_mg_scatter = b.add(d->mg_scatter, ng);
+  h.off_mg_fission = b.add(d->mg_fission, ng);
+  h.off_mg_nubar = b.add(d->mg_nubar, ng);
+  h.off_mg_scatter_probs = b.add(d->mg_scatter_probs, ng * G);
+  h.off_mg_chi = b.add(d->mg_chi, ng * G);
+  b.pad();
+  h.total_bytes = static_cast<uint32_t>(b.bytes.size());
+  b.header() = h;
+
+  auto* w = new mmc_world;
+  w->device = device;
+  w->header = h;
+  w->blob_bytes = h.total_bytes;
+  for (int n = 0; n < d->n_nuclides; n++) w->has_fission = w->has_fission || (d->mg_reaction_mask[n] & MMC_REACTION_FISSION);
+  cudaDeviceProp prop{};
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) e = cudaMalloc(&w->d_blob, w->blob_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(w->d_blob, b.bytes.data(), w->blob_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&w->d_next, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    mmc_world_destroy(w);
+    return fail(MMC_ERR_CUDA, "mmc_world_create: %s", cudaGetErrorString(e));
+  }
+  w->sm_count = prop.multiProcessorCount;
+  w->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = w;
+  return MMC_OK;
+}
+
+void mmc_world_destroy(mmc_world* w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  cudaFree(w->d_blob);
+  cudaFree(w->d_sites);
+  cudaFree(w->d_pending);
+  cudaFree(w->d_bounds);
+  cudaFree(w->d_next);
+  delete w;
+}
+
+int mmc_fixed_source_run_device(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators, int32_t n_estimators,
+    uint64_t seed0, uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, uint64_t* d_scores,
+    uint64_t* d_square_scores, mmc_counters* d_counters) {
+  auto* w = const_cast<mmc_world*>(world);
+  Prepared p;
+  if (int s = prepare_run(w, source, estimators, n_estimators, seed0, first_history, n_histories, options, false, p)) return s;
+  if (!d_counters) return fail(MMC_ERR_INVALID, "d_counters is NULL");
+  if (p.run.total_bins && (!d_scores || !d_square_scores)) return fail(MMC_ERR_INVALID, "tally buffers are NULL");
+  MMC_CUDA(cudaSetDevice(w->device));
+  if (n_histories == 0) return MMC_OK;
+  const size_t threads = static_cast<size_t>(p.cfg.blocks) * kThreadsPerBlock;
+  if (int s = ensure_scratch(w, threads, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
+  if (!p.bounds.empty())
+    MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), p.stream));
+  MMC_CUDA(launch_fixed_source(
+      p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
+      reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,
+      p.stream));
+  return MMC_OK;
+}
+
+int mmc_fixed_source_run(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators, int32_t n_estimators,
+    uint64_t seed0, uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, double* scores,
+    double* square_scores, mmc_counters* counters) {
+  if (!world) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  uint64_t total_bins = 0;
+  for (int e = 0; e < n_estimators && estimators; e++) total_bins += mmc_estimator_size(&estimators[e]);
+  if (total_bins && (!scores || !square_scores)) return fail(MMC_ERR_INVALID, "scores / square_scores is NULL");
+  MMC_CUDA(cudaSetDevice(world->device));
+  mmc_run_options opt{};
+  if (options) opt = *options;
+  opt.struct_size = sizeof(mmc_run_options);
+  cudaStream_t stream = opt.stream ? static_cast<cudaStream_t>(opt.stream) : world->stream;
+  unsigned long long* d_tally = nullptr;
+  mmc_counters* d_counters = nullptr;
+  const size_t tally_bytes = std::max<uint64_t>(total_bins, 1) * 2 * sizeof(unsigned long long);
+  MMC_CUDA(cudaMalloc(&d_tally, tally_bytes));
+  cudaError_t e = cudaMalloc(&d_counters, sizeof(mmc_counters));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_tally, 0, tally_bytes, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_counters, 0, sizeof(mmc_counters), stream);
+  int status = MMC_OK;
+  if (e != cudaSuccess) status = fail(MMC_ERR_CUDA, "mmc_fixed_source_run: %s", cudaGetErrorString(e));
+  if (status == MMC_OK)
+    status = mmc_fixed_source_run_device(
+        world, source, estimators, n_estimators, seed0, first_history, n_histories, &opt,
+        reinterpret_cast<uint64_t*>(d_tally), reinterpret_cast<uint64_t*>(d_tally + total_bins), d_counters);
+  std::vector<unsigned long long> h_tally(std::max<uint64_t>(total_bins, 1) * 2);
+  mmc_counters h_counters{};
+  if (status == MMC_OK) {
+    e = cudaMemcpyAsync(h_tally.data(), d_tally, tally_bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_counters, d_counters, sizeof(mmc_counters), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) status = fail(MMC_ERR_CUDA, "mmc_fixed_source_run: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_tally);
+  cudaFree(d_counters);
+  if (status != MMC_OK) return status;
+  // Scorable::operator+= (Scorable.cpp:37-48): integer-valued, exact below 2^53
+  for (uint64_t i = 0; i < total_bins; i++) {
+    scores[i] += static_cast<double>(h_tally[i]);
+    square_scores[i] += static_cast<double>(h_tally[total_bins + i]);
+  }
+  if (counters) *counters = h_counters;
+  return status_from_counters(h_counters);
+}
+
+int mmc_trace_histories(
+    const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
+    const mmc_run_options* options, mmc_event_record* records, size_t cap, size_t* n_records) {
+  auto* w = const_cast<mmc_world*>(world);
+  Prepared p;
+  if (int s = prepare_run(w, source, nullptr, 0, seed0, first_history, n_histories, options, true, p)) return s;
+  if (!records || !n_records) return fail(MMC_ERR_INVALID, "records / n_records is NULL");
+  *n_records = 0;
+  MMC_CUDA(cudaSetDevice(w->device));
+  // the single trace thread gets a roomy secondary queue
+  p.run.secondary_capacity = std::max<uint32_t>(p.run.secondary_capacity, 1024);
+  if (int s = ensure_scratch(w, 1, p.run.secondary_capacity, 1, 0)) return s;
+  mmc_event_record* d_records = nullptr;
+  unsigned long long* d_n = nullptr;
+  mmc_counters* d_counters = nullptr;
+  MMC_CUDA(cudaMalloc(&d_records, std::max<size_t>(cap, 1) * sizeof(mmc_event_record)));
+  cudaError_t e = cudaMalloc(&d_n, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(mmc_counters));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_counters, 0, sizeof(mmc_counters), p.stream);
+  if (e == cudaSuccess)
+    e = launch_trace(w->d_blob, p.run, w->d_sites, d_records, cap, d_n, d_counters, p.stream);
+  unsigned long long n = 0;
+  mmc_counters h_counters{};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, p.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, p.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p.stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(records, d_records, std::min<size_t>(n, cap) * sizeof(mmc_event_record), cudaMemcpyDeviceToHost);
+  cudaFree(d_records);
+  cudaFree(d_n);
+  cudaFree(d_counters);
+  if (e != cudaSuccess) return fail(MMC_ERR_CUDA, "mmc_trace_histories: %s", cudaGetErrorString(e));
+  *n_records = static_cast<size_t>(std::min<unsigned long long>(n, cap));
+  if (n > cap) return fail(MMC_ERR_CAPACITY, "trace needs %llu records but cap is %zu", n, cap);
+  return status_from_counters(h_counters);
+}
+
+}  // extern "C"

@@ -1,0 +1,334 @@
+// sm_100a kernels of the history transport loop.
+//
+// fixed_source_kernel: one fused, persistent kernel that replaces
+// FixedSource::StartWorker (FixedSource.cpp:40-77).  Particle state lives in
+// registers for its whole life; the world tables are staged once per CTA into
+// shared memory.  Lanes whose history has ended are refilled in place: every
+// loop iteration first tops the warp up with new histories (claimed in chunks
+// from one global counter with a single atomic per chunk, handed out with
+// ballot/popc), then every lane advances its particle by exactly one event.
+// That keeps all 32 lanes on the expensive fp64 event code instead of idling
+// until the longest history of the warp finishes.
+//
+// Tallies: the `current` score is 0/1 per event, so Sigma s and
+// Sigma_h (Sigma_e s)^2 are integers.  Each lane keeps the per-history pending
+// table of ScorableProxy (Scorable.cpp:81-99) as (bin, hits) pairs in a private
+// slice of global scratch; the k-th hit of a history in a bin adds 1 to
+// scores[bin] and k^2-(k-1)^2 = 2k-1 to square_scores[bin], which is what
+// CommitHistory (Scorable.cpp:101-106) yields after the history.  Lanes that
+// hit the same bin in the same iteration are combined with __match_any_sync and
+// one 64-bit integer atomic per distinct bin; integer sums make the result
+// independent of scheduling, GPU count and atomic ordering.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "transport.cuh"
+
+namespace mmc {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void load_site(const BankSite& s, Particle& p) {
+  p.px = s.position[0];
+  p.py = s.position[1];
+  p.pz = s.position[2];
+  p.dx = s.direction[0];
+  p.dy = s.direction[1];
+  p.dz = s.direction[2];
+  p.group = s.energy_bits;
+  p.rng.x = lcg_seed(s.seed);
+  p.cell = -1;
+  p.surface = -1;
+  p.event = MMC_EV_BIRTH;
+}
+
+struct ThreadCounters {
+  uint32_t histories = 0, births = 0, events = 0, collisions = 0, crossings = 0, virtuals = 0, scores = 0,
+           secondaries = 0, lost = 0, capacity = 0, physics = 0;
+};
+
+__device__ __forceinline__ void count_event(ThreadCounters& c, const Particle& p, const StepOut& o) {
+  c.events++;
+  c.collisions += (p.event == MMC_EV_SCATTER || p.event == MMC_EV_CAPTURE || p.event == MMC_EV_FISSION) &&
+                  !o.error_physics;
+  c.crossings += (p.event == MMC_EV_SURFACE_CROSS || p.event == MMC_EV_LEAK) && !o.error_physics;
+  c.virtuals += p.event == MMC_EV_VIRTUAL_COLLISION;
+  c.secondaries += o.secondaries;
+  c.lost += o.error_lost;
+  c.capacity += o.error_capacity;
+  c.physics += o.error_physics;
+}
+
+__device__ __forceinline__ void flush_counter(uint64_t* dst, uint32_t v) {
+  v = __reduce_add_sync(kFull, v);
+  if ((threadIdx.x & 31) == 0 && v)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(v));
+}
+
+// Stage the world blob into shared memory (16-byte vectors).
+__device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t bytes, bool in_smem, char* smem) {
+  if (!in_smem) return world_g;
+  const uint4* src = reinterpret_cast<const uint4*>(world_g);
+  uint4* dst = reinterpret_cast<uint4*>(smem);
+  for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return smem;
+}
+
+}  // namespace
+
+template <int kTracking>
+__global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
+    BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
+    unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters) {
+  extern __shared__ __align__(16) char smem[];
+  const WorldView w(stage_world(world_g, run.world_bytes, run.world_in_smem != 0, smem));
+
+  const uint32_t lane = threadIdx.x & 31;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  SiteDeque dq;
+  dq.slots = site_scratch + tid * run.secondary_capacity;
+  dq.mask = run.secondary_capacity - 1;
+  dq.head = 0;
+  dq.count = 0;
+  uint2* pending = pending_scratch + tid * run.pending_capacity;
+  uint32_t n_pending = 0;
+
+  Particle p;
+  p.event = MMC_EV_CAPTURE;  // "dead": forces a refill
+  bool done = false;         // no more work for this lane
+  uint64_t w_next = 0, w_end = 0;  // warp-uniform chunk of history indices
+  ThreadCounters c;
+
+  while (true) {
+    // ---- refill: next particle of the current history, else a new history
+    bool alive = is_alive(p.event);
+    if (!alive && !done && !dq.empty()) {
+      // bank.back(): FixedSource.cpp:63-71
+      dq.count--;
+      load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
+      alive = true;
+      c.births++;
+    }
+    const bool need = !alive && !done;
+    const unsigned need_mask = __ballot_sync(kFull, need);
+    if (need_mask) {
+      const uint32_t n = __popc(need_mask);
+      const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
+      const uint64_t avail = w_end - w_next;
+      uint64_t idx;
+      bool valid;
+      if (n > avail) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next_history, static_cast<unsigned long long>(run.chunk));
+        base = __shfl_sync(kFull, base, 0);
+        const uint64_t new_begin = base < run.n_histories ? base : run.n_histories;
+        const uint64_t new_end = base + run.chunk < run.n_histories ? base + run.chunk : run.n_histories;
+        if (rank < avail) {
+          idx = w_next + rank;
+          valid = true;
+        } else {
+          idx = new_begin + (rank - avail);
+          valid = idx < new_end;
+        }
+        w_next = new_begin + (n - avail);
+        w_end = new_end;
+        if (w_next > w_end) w_next = w_end;
+      } else {
+        idx = w_next + rank;
+        valid = true;
+        w_next += n;
+      }
+      if (need) {
+        if (valid) {
+          // scoring_proxy of the previous history is committed (incrementally);
+          // a new proxy starts empty: FixedSource.cpp:48
+          n_pending = 0;
+          sample_source(run.source, run.seed0 + run.first_history + idx, p);
+          alive = true;
+          c.histories++;
+          c.births++;
+        } else {
+          done = true;
+        }
+      }
+    }
+    if (__all_sync(kFull, done)) break;
+
+    // ---- one event per live lane
+    StepOut o;
+    o.secondaries = 0;
+    o.error_physics = o.error_capacity = o.error_lost = false;
+    if (alive) {
+      if (p.cell < 0) {
+        // TransportMethod.cpp:55: p.SetCell(w.FindCellContaining(p.GetPosition()))
+        p.cell = find_cell(w, p.px, p.py, p.pz);
+        if (p.cell < 0) {
+          o.error_lost = true;
+          p.event = MMC_EV_LEAK;
+        }
+      }
+      if (p.cell >= 0) transport_step<kTracking>(w, p, dq, o);
+      count_event(c, p, o);
+    }
+
+    // ---- EstimatorSetProxy::Score(p): TransportMethod.cpp:74
+    for (int32_t e = 0; e < run.n_estimators; e++) {
+      uint64_t bin = 0;
+      const bool hit = alive && !o.error_lost && estimator_score(run.estimators[e], bounds, p, bin);
+      const unsigned hit_mask = __ballot_sync(kFull, hit);
+      if (hit) {
+        // hits of this history in this bin so far
+        uint32_t k = 0, slot = 0;
+        for (; slot < n_pending; slot++)
+          if (pending[slot].x == static_cast<uint32_t>(bin)) break;
+        if (slot < n_pending) {
+          k = pending[slot].y;
+          pending[slot].y = k + 1;
+        } else if (n_pending < run.pending_capacity) {
+          pending[n_pending++] = make_uint2(static_cast<uint32_t>(bin), 1u);
+        } else {
+          c.capacity++;
+        }
+        c.scores++;
+        const unsigned peers = __match_any_sync(hit_mask, bin);
+        const uint32_t sq = __reduce_add_sync(peers, 2u * k + 1u);
+        if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
+          atomicAdd(scores + bin, static_cast<unsigned long long>(__popc(peers)));
+          atomicAdd(square_scores + bin, static_cast<unsigned long long>(sq));
+        }
+      }
+    }
+  }
+
+  flush_counter(&counters->n_histories, c.histories);
+  flush_counter(&counters->n_births, c.births);
+  flush_counter(&counters->n_events, c.events);
+  flush_counter(&counters->n_collisions, c.collisions);
+  flush_counter(&counters->n_crossings, c.crossings);
+  flush_counter(&counters->n_virtual, c.virtuals);
+  flush_counter(&counters->n_scores, c.scores);
+  flush_counter(&counters->n_secondaries, c.secondaries);
+  flush_counter(&counters->n_lost, c.lost);
+  flush_counter(&counters->n_capacity_overflow, c.capacity);
+  flush_counter(&counters->n_physics_errors, c.physics);
+}
+
+// Parity hook: one thread walks histories sequentially and records every event
+// in the reference's order (see mmc_trace_histories).
+template <int kTracking>
+__global__ void trace_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ RunSpec run, BankSite* site_scratch,
+    mmc_event_record* records, unsigned long long cap, unsigned long long* n_records, mmc_counters* counters) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const WorldView w(world_g);
+  SiteDeque dq;
+  dq.slots = site_scratch;
+  dq.mask = run.secondary_capacity - 1;
+  unsigned long long n = 0;
+  ThreadCounters c;
+  auto emit = [&](uint64_t history, uint32_t particle, const Particle& p) {
+    if (n < cap) {
+      mmc_event_record& r = records[n];
+      r.history = history;
+      r.particle = particle;
+      r.event = p.event;
+      r.group = p.group;
+      r.energy = 0.0;
+      r.cell = p.cell;
+      r.surface = p.surface;
+      r.position[0] = p.px;
+      r.position[1] = p.py;
+      r.position[2] = p.pz;
+      r.direction[0] = p.dx;
+      r.direction[1] = p.dy;
+      r.direction[2] = p.dz;
+      r.rng_state = p.rng.x;
+    }
+    n++;
+  };
+  for (uint64_t h = 0; h < run.n_histories; h++) {
+    const uint64_t history = run.first_history + h;
+    dq.head = 0;
+    dq.count = 0;
+    Particle p;
+    sample_source(run.source, run.seed0 + history, p);
+    c.histories++;
+    uint32_t ordinal = 0;
+    while (true) {
+      c.births++;
+      emit(history, ordinal, p);
+      StepOut o;
+      p.cell = find_cell(w, p.px, p.py, p.pz);
+      if (p.cell < 0) {
+        c.lost++;
+      } else {
+        while (is_alive(p.event)) {
+          transport_step<kTracking>(w, p, dq, o);
+          count_event(c, p, o);
+          emit(history, ordinal, p);
+        }
+      }
+      if (dq.empty()) break;
+      dq.count--;
+      load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
+      ordinal++;
+    }
+  }
+  *n_records = n;
+  counters->n_histories = c.histories;
+  counters->n_births = c.births;
+  counters->n_events = c.events;
+  counters->n_collisions = c.collisions;
+  counters->n_crossings = c.crossings;
+  counters->n_virtual = c.virtuals;
+  counters->n_secondaries = c.secondaries;
+  counters->n_lost = c.lost;
+  counters->n_capacity_overflow = c.capacity;
+  counters->n_physics_errors = c.physics;
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t launch_fixed_source(
+    const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
+    uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
+    unsigned long long* square_scores, mmc_counters* counters, cudaStream_t stream) {
+  const size_t smem = run.world_in_smem ? run.world_bytes : 0;
+  auto go = [&](auto kernel) -> cudaError_t {
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kernel<<<cfg.blocks, kThreadsPerBlock, smem, stream>>>(
+        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters);
+    return cudaGetLastError();
+  };
+  if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA>);
+  return go(fixed_source_kernel<MMC_TRACK_SURFACE>);
+}
+
+cudaError_t launch_trace(
+    const char* world_d, const RunSpec& run, BankSite* site_scratch, mmc_event_record* records, unsigned long long cap,
+    unsigned long long* n_records, mmc_counters* counters, cudaStream_t stream) {
+  if (run.tracking == MMC_TRACK_CELL_DELTA)
+    trace_kernel<MMC_TRACK_CELL_DELTA><<<1, 1, 0, stream>>>(world_d, run, site_scratch, records, cap, n_records, counters);
+  else
+    trace_kernel<MMC_TRACK_SURFACE><<<1, 1, 0, stream>>>(world_d, run, site_scratch, records, cap, n_records, counters);
+  return cudaGetLastError();
+}
+
+int max_blocks_per_sm(int tracking, size_t smem) {
+  int n = 0;
+  if (tracking == MMC_TRACK_CELL_DELTA)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fixed_source_kernel<MMC_TRACK_CELL_DELTA>, kThreadsPerBlock, smem);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fixed_source_kernel<MMC_TRACK_SURFACE>, kThreadsPerBlock, smem);
+  return n;
+}
+
+}  // namespace mmc

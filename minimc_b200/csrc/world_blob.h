@@ -1,0 +1,92 @@
+// Flat device image of the reference's `const World` (World.hpp) plus the
+// source and estimator descriptors of one run.  One contiguous, 16-byte aligned
+// byte blob: a fixed header of counts and byte offsets followed by SoA arrays.
+// The transport kernels stage the whole blob into shared memory when it fits
+// (every multigroup deck of the reference is < 2 KB) and otherwise read it
+// through the read-only path from global memory / L2.
+#pragma once
+
+#include <cstdint>
+
+namespace mmc {
+
+constexpr int kMaxEstimators = 16;
+
+struct BinsSpec {
+  int32_t kind;        // mmc_bins_kind
+  uint32_t n_bins;     // including the two unbounded end bins
+  double lower, upper, width, base;
+  uint32_t off_boundaries;  // byte offset of double[n_bins-1] (BOUNDARIES)
+  uint32_t pad;
+};
+
+struct EstimatorSpec {
+  int32_t surface;
+  int32_t has_direction;
+  double direction[3];   // normalised (Direction ctor, Point.cpp:80-83)
+  BinsSpec cosine, energy;
+  uint64_t stride;       // ParticleBins::strides[0] = energy.n_bins (Bins.hpp:150-153)
+  uint64_t offset;       // first bin of this estimator in the concatenated score arrays
+};
+
+struct SourceSpec {
+  double position[3];
+  double direction[3];   // normalised
+  int32_t direction_kind;
+  int32_t pad;
+  uint64_t group;
+  double energy;
+};
+
+struct WorldHeader {
+  uint32_t total_bytes;
+  int32_t n_surfaces, n_cells, n_materials, n_nuclides, n_groups;
+  int32_t pad0;
+  // byte offsets from the start of the blob
+  uint32_t off_surface_type;    // int32[n_surfaces]
+  uint32_t off_surface_param;   // double[n_surfaces][4]
+  uint32_t off_cell_material;   // int32[n_cells]
+  uint32_t off_cell_surf_begin; // int32[n_cells+1]
+  uint32_t off_cell_surf;       // int32[nnz]  (index << 1) | sense
+  uint32_t off_cell_field_kind; // int32[n_cells]
+  uint32_t off_cell_field_param;// double[n_cells][6]
+  uint32_t off_mat_aden;        // double[n_materials]
+  uint32_t off_mat_nuc_begin;   // int32[n_materials+1]
+  uint32_t off_mat_nuc_index;   // int32[nnz]
+  uint32_t off_mat_nuc_afrac;   // double[nnz]
+  uint32_t off_mg_mask;         // uint32[n_nuclides]
+  uint32_t off_mg_total;        // double[n_nuclides][G]
+  uint32_t off_mg_capture, off_mg_scatter, off_mg_fission, off_mg_nubar;
+  uint32_t off_mg_scatter_probs, off_mg_chi;  // double[n_nuclides][G][G]
+  uint32_t pad1;
+};
+
+// Per-run constant block (passed by value as a kernel parameter).
+struct RunSpec {
+  SourceSpec source;
+  EstimatorSpec estimators[kMaxEstimators];
+  int32_t n_estimators;
+  int32_t tracking;
+  uint64_t seed0;
+  uint64_t first_history;
+  uint64_t n_histories;
+  uint64_t total_bins;
+  uint32_t secondary_capacity;  // power of two
+  uint32_t pending_capacity;
+  uint32_t chunk;               // histories claimed per warp refill
+  uint32_t world_bytes;         // size of the world blob (multiple of 16)
+  uint32_t world_in_smem;       // 1: kernels stage the blob into shared memory
+  uint32_t pad;
+};
+
+// One banked particle (secondary or k-eigenvalue site): 64 bytes.
+struct BankSite {
+  double position[3];
+  double direction[3];
+  uint64_t energy_bits;  // group (multigroup) or the bits of the energy in MeV
+  uint32_t seed;         // argument of std::minstd_rand{seed} (Particle.cpp:96-100)
+  int32_t surface;       // unused for secondaries (Particle::current_surface starts null)
+};
+static_assert(sizeof(BankSite) == 64, "BankSite must be 64 bytes");
+
+}  // namespace mmc

@@ -1,0 +1,80 @@
+"""Shared helpers of the test-suite: deck -> oracle problem / product objects."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+from minimc_b200 import capi, decks
+from oracle import flatten as oflatten
+from oracle import port_py
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REFERENCE_ROOT = Path("/root/reference")
+
+
+def flat_from_xml(text: str) -> dict:
+    return oflatten.flatten(text, is_text=True)
+
+
+def oracle_problem(flat: dict) -> port_py.Problem:
+    return port_py.Problem(flat)
+
+
+def product_world(flat: dict) -> capi.World:
+    w = flat["world"]
+    return capi.World(capi.FlatWorld(**w))
+
+
+def product_source(flat: dict) -> capi.SourceDesc:
+    s = flat["source"]
+    return capi.source_desc(position=s["position"], direction_kind=s["direction_kind"], direction=s["direction"],
+                            group=s["group"])
+
+
+def product_estimators(flat: dict) -> capi.Estimators:
+    specs = []
+    for e in flat["estimators"]:
+        def conv(b):
+            if b["kind"] == 0:
+                return (capi.BINS_NONE, {})
+            if b["kind"] in (1, 2):
+                return (b["kind"], {"bins": b["n_bins"] - 2, "lower": b["lower"], "upper": b["upper"],
+                                    "base": b.get("base", 10.0)})
+            return (capi.BINS_BOUNDARIES, {"boundaries": b["boundaries"]})
+        specs.append({"surface": e["surface"], "cosine_direction": e["cosine_direction"], "cosine": conv(e["cosine"]),
+                      "energy": conv(e["energy"])})
+    return capi.Estimators(specs)
+
+
+def record_tuple(r, with_cell=True):
+    """(history, particle, event, group, cell, surface, rng_state) of a ctypes record or parsed dict."""
+    if isinstance(r, dict):
+        t = (r["history"], r["particle"], r["event"], r["group"], r["cell"], r["surface"], r["rng_state"])
+    else:
+        t = (int(r.history), int(r.particle), int(r.event), int(r.group), int(r.cell), int(r.surface),
+             int(r.rng_state))
+    if not with_cell or t[2] == 0:  # the cell of a birth record is not part of the contract
+        t = t[:4] + (None,) + t[5:]
+    return t
+
+
+def record_vectors(r):
+    if isinstance(r, dict):
+        return np.array(r["position"]), np.array(r["direction"])
+    return np.array(list(r.position)), np.array(list(r.direction))
+
+
+def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Distance in units in the last place between float64 arrays (same sign assumed near zero)."""
+    ia = np.ascontiguousarray(a, np.float64).view(np.int64)
+    ib = np.ascontiguousarray(b, np.float64).view(np.int64)
+    ia = np.where(ia < 0, np.int64(-(2 ** 63)) - ia, ia)
+    ib = np.where(ib < 0, np.int64(-(2 ** 63)) - ib, ib)
+    return np.abs(ia - ib)
+
+
+def load_golden(name: str):
+    with open(GOLDEN / name) as f:
+        return json.load(f)
