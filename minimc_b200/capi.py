@@ -98,6 +98,7 @@ class RunOptions(C.Structure):
 EXPORTS = (
     "mmc_abi_version", "mmc_last_error", "mmc_device_count", "mmc_world_create", "mmc_world_destroy",
     "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_device", "mmc_trace_histories",
+    "mmc_test_device_math",
 )
 
 _lib = None
@@ -140,6 +141,8 @@ def load() -> C.CDLL:
     lib.mmc_trace_histories.argtypes = [
         C.c_void_p, C.POINTER(SourceDesc), C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(RunOptions),
         C.POINTER(EventRecord), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.mmc_test_device_math.restype = C.c_int
+    lib.mmc_test_device_math.argtypes = [C.c_int, _pd, _pd, _pd, C.c_size_t]
     if lib.mmc_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mmc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -257,6 +260,15 @@ class Estimators:
             self._keep += [k1, k2]
             self.sizes.append(int(e.cosine.n_bins * e.energy.n_bins))
         self.total_bins = sum(self.sizes)
+
+
+def device_math(fn: int, x):
+    """mmc_test_device_math: (out0, out1) evaluated on the GPU."""
+    x = _arr(x, np.float64)
+    out0, out1 = np.zeros_like(x), np.zeros_like(x)
+    check(load().mmc_test_device_math(fn, _ptr(x, C.c_double), _ptr(out0, C.c_double), _ptr(out1, C.c_double),
+                                      x.size))
+    return out0, out1
 
 
 class World:

@@ -517,4 +517,23 @@ int mmc_trace_histories(
   return status_from_counters(h_counters);
 }
 
+int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n) {
+  if (fn < 0 || fn > 4 || !x || !out0 || (fn == 1 && !out1)) return fail(MMC_ERR_INVALID, "bad arguments");
+  if (mmc_device_count() < 1) return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible");
+  if (n == 0) return MMC_OK;
+  double *d_x = nullptr, *d_0 = nullptr, *d_1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_x, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_0, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_1, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_test_math(fn, d_x, d_0, d_1, n, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out0, d_0, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && fn == 1) e = cudaMemcpy(out1, d_1, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_x);
+  cudaFree(d_0);
+  cudaFree(d_1);
+  if (e != cudaSuccess) return fail(MMC_ERR_CUDA, "mmc_test_device_math: %s", cudaGetErrorString(e));
+  return MMC_OK;
+}
+
 }  // extern "C"

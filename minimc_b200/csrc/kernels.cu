@@ -293,6 +293,28 @@ __global__ void trace_kernel(
   counters->n_physics_errors = c.physics;
 }
 
+__global__ void test_math_kernel(int fn, const double* x, double* out0, double* out1, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (fn == 0) {
+    out0[i] = glibc::log(x[i]);
+  } else if (fn == 1) {
+    glibc::sincos(x[i], &out0[i], &out1[i]);
+  } else if (fn == 2) {
+    out0[i] = glibc::sin(x[i]);
+  } else if (fn == 3) {
+    out0[i] = glibc::cos(x[i]);
+  } else {
+    Rng rng{lcg_seed(static_cast<uint64_t>(x[i]))};
+    out0[i] = rng.canonical();
+  }
+}
+
+cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* out1_d, size_t n, cudaStream_t stream) {
+  test_math_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(fn, x_d, out0_d, out1_d, n);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ launchers
 cudaError_t launch_fixed_source(
     const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,

@@ -24,6 +24,8 @@ cudaError_t launch_trace(
     const char* world_d, const RunSpec& run, BankSite* site_scratch, mmc_event_record* records, unsigned long long cap,
     unsigned long long* n_records, mmc_counters* counters, cudaStream_t stream);
 
+cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* out1_d, size_t n, cudaStream_t stream);
+
 // occupancy query for the fused kernel
 int max_blocks_per_sm(int tracking, size_t smem);
 

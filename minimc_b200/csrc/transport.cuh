@@ -3,14 +3,16 @@
 // arithmetic it must reproduce operation for operation: this translation unit
 // is compiled with -fmad=false so that each + - * / sqrt is one IEEE-754
 // round-to-nearest operation, exactly as g++ emits for baseline x86-64
-// (SURVEY.md F5, H1).  Only log / sin / cos may differ from glibc in the last
-// ulp; they feed positions and directions, never integer bookkeeping.
+// (SURVEY.md F5, H1).  log / sincos / sin / cos are glibc's, restated bit for
+// bit in glibc_math.h, because the reference's absolute 10-eps surface nudge
+// makes cell assignment depend on the last bit of a position.
 #pragma once
 
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "../../include/minimc_b200.h"
+#include "glibc_math.h"
 #include "world_blob.h"
 
 namespace mmc {
@@ -87,7 +89,7 @@ __device__ __forceinline__ void isotropic_direction(Rng& rng, double& x, double&
   const double sin_theta = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(x, x)));
   const double phi = __dmul_rn(rng.canonical(), 6.283185307179586476925286766559);
   double s, c;
-  sincos(phi, &s, &c);
+  glibc::sincos(phi, &s, &c);  // g++ -O3 merges the reference's cos/sin pair into one sincos call
   y = __dmul_rn(sin_theta, c);
   z = __dmul_rn(sin_theta, s);
 }
@@ -115,8 +117,8 @@ __device__ inline void rotate_direction(
   double vy = __dsub_rn(__dmul_rn(dz, ux), __dmul_rn(dx, uz));
   double vz = __dsub_rn(__dmul_rn(dx, uy), __dmul_rn(dy, ux));
   normalize(vx, vy, vz);
-  double s, c;
-  sincos(phi, &s, &c);
+  // separate cos and sin calls in the reference's object code (Point.cpp:117-118)
+  const double c = glibc::cos(phi), s = glibc::sin(phi);
   const double sq = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(mu, mu)));
   const double uc = __dmul_rn(sq, c), vc = __dmul_rn(sq, s);
   // (u_comp + v_comp) + d_comp, then Direction(Point&&) normalises
@@ -426,7 +428,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
   const double micro = material_micro_total(w, mat, p.group);
   const double lambda = __dmul_rn(w.at<double>(w.h->off_mat_aden)[mat], micro);
   // std::exponential_distribution: -log(1 - u) / lambda
-  const double d_coll = __ddiv_rn(-log(__dsub_rn(1.0, p.rng.canonical())), lambda);
+  const double d_coll = __ddiv_rn(-glibc::log(__dsub_rn(1.0, p.rng.canonical())), lambda);
   int32_t nearest;
   const double d_surf = nearest_surface(w, p, nearest);
   bool cross;
@@ -463,7 +465,7 @@ __device__ __forceinline__ uint64_t bins_index(const BinsSpec& b, const double* 
     if (v >= b.upper) return b.n_bins - 1;
     return static_cast<uint64_t>(__dadd_rn(__ddiv_rn(__dsub_rn(v, b.lower), b.width), 1.0));
   case MMC_BINS_LOGSPACE: {
-    const double lv = __ddiv_rn(log(v), log(b.base));
+    const double lv = __ddiv_rn(glibc::log(v), glibc::log(b.base));
     if (lv < b.lower) return 0;
     if (lv >= b.upper) return b.n_bins - 1;
     return static_cast<uint64_t>(__dadd_rn(__ddiv_rn(__dsub_rn(lv, b.lower), b.width), 1.0));

@@ -78,3 +78,38 @@ def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 def load_golden(name: str):
     with open(GOLDEN / name) as f:
         return json.load(f)
+
+
+TRACKING = {"surface": None, "delta": "cell delta"}
+DECK_CASES = [(name, trk) for name in decks.DECKS for trk in TRACKING]
+TRACE_HISTORIES = 48
+
+
+def deck_text(name: str, tracking: str, **kw) -> str:
+    if name == "three_shells":
+        kw.setdefault("estimators", decks.THREE_SHELL_ESTIMATORS)
+    return decks.DECKS[name](tracking=TRACKING[tracking], **kw)
+
+
+def golden_trace(name: str, tracking: str):
+    return port_py.parse_trace((GOLDEN / f"{name}__{tracking}.trace").read_text())
+
+
+def golden_out(name: str, tracking: str):
+    return port_py.parse_out((GOLDEN / f"{name}__{tracking}.out").read_text())
+
+
+def format_out_values(flat: dict, scores, squares):
+    """Formats scores the way Scorable::GetScoreAsString does (Scorable.cpp:51-70): mean = score / N,
+    std dev = sqrt(square - score^2 / N) / N, both printed with std::scientific (%e)."""
+    N = float(flat["run"]["histories"])
+    result, off = {}, 0
+    for e in flat["estimators"]:
+        n = e["n_bins"]
+        sc, sq = scores[off:off + n], squares[off:off + n]
+        result[e["name"]] = {
+            "mean": ["%e" % (v / N) for v in sc],
+            "std dev": ["%e" % (np.sqrt(q - v * v / N) / N) for v, q in zip(sc, sq)],
+        }
+        off += n
+    return result
