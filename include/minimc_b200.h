@@ -61,6 +61,68 @@ enum { MMC_REACTION_CAPTURE = 1, MMC_REACTION_SCATTER = 2, MMC_REACTION_FISSION 
 /* ScalarField.cpp:35-58 */
 typedef enum mmc_field_kind { MMC_FIELD_CONSTANT = 0, MMC_FIELD_LINEAR = 1 } mmc_field_kind;
 
+/* ---- continuous-energy tables (n_groups == 0) -------------------------------
+ * Every pointwise table is the sorted, de-duplicated key/value content of the
+ * std::map behind ContinuousMap (ContinuousMap.hpp:21-56): x strictly
+ * increasing, lin-lin interpolation, clamped at both ends. */
+typedef struct mmc_table1d {
+  uint64_t n;
+  const double* x;                  /* [n] */
+  const double* y;                  /* [n] */
+} mmc_table1d;
+
+/* ThermalScattering::BetaPartition / AlphaPartition (ThermalScattering.hpp:62-100):
+ * value(cdf_index, grid_index, T) = lerp_T( sum_r S[r] * CDF_modes[cdf][r] * grid_T_modes[grid][T_k][r] ).
+ * Layouts are the row-major HDF5DataSet<D> layouts (HDF5DataSet.hpp:152-167). */
+typedef struct mmc_tsl_partition {
+  uint64_t n_cdf, n_grid, n_temperature, rank;
+  const double* cdf;                /* [n_cdf]   CDF_modes.GetAxis(0): the F values */
+  const double* grid;               /* [n_grid]  E_T_modes / beta_T_modes .GetAxis(0): incident E (MeV) or beta */
+  const double* temperature;        /* [n_temperature] .GetAxis(1) */
+  const double* cdf_modes;          /* [n_cdf][rank] */
+  const double* singular_values;    /* [rank] */
+  const double* grid_T_modes;       /* [n_grid][n_temperature][rank] */
+} mmc_tsl_partition;
+
+/* ThermalScattering (ThermalScattering.cpp:24-104). */
+typedef struct mmc_tsl_desc {
+  mmc_table1d majorant;             /* ThermalScattering::majorant */
+  uint64_t n_energy, n_temperature, rank;
+  const double* energy;             /* [n_energy]      scatter_xs_E.GetAxis(0); cutoff_energy = last */
+  const double* temperature;        /* [n_temperature] scatter_xs_T.GetAxis(0) */
+  const double* xs_E;               /* [n_energy][rank] */
+  const double* xs_S;               /* [rank] */
+  const double* xs_T;               /* [n_temperature][rank] */
+  int32_t n_beta_partitions, n_alpha_partitions;
+  const mmc_tsl_partition* beta_partitions;
+  const mmc_tsl_partition* alpha_partitions;
+  double beta_cutoff, alpha_cutoff;
+  double awr;                       /* ThermalScattering::awr (the nuclide's) */
+} mmc_tsl_desc;
+
+/* One ContinuousReaction (ContinuousReaction.cpp:41-265), in XML document order. */
+typedef struct mmc_ce_reaction {
+  int32_t kind;                     /* MMC_REACTION_CAPTURE / _SCATTER / _FISSION */
+  mmc_table1d xs;                   /* evaluation.xs */
+  double temperature;               /* evaluation.temperature */
+  const mmc_tsl_desc* tsl;          /* scatter only; NULL when the deck has no <tsl> */
+  int32_t has_nubar;                /* fission only */
+  mmc_table1d nubar;
+} mmc_ce_reaction;
+
+/* One Continuous interaction (Continuous.cpp:22-90). */
+typedef struct mmc_ce_nuclide {
+  double awr;                       /* <nuclide awr=...> */
+  mmc_table1d total;                /* Continuous::total.xs */
+  double total_temperature;
+  int32_t n_reactions;
+  const mmc_ce_reaction* reactions; /* [n_reactions] */
+} mmc_ce_nuclide;
+
+typedef struct mmc_ce_desc {
+  const mmc_ce_nuclide* nuclides;   /* [mmc_world_desc.n_nuclides] */
+} mmc_ce_desc;
+
 /* Flattened `const World` (World.hpp).  Index order is the reference's:
  * surfaces / nuclides / materials in World creation order (World.cpp:89-168),
  * cells in XML order (first match wins, World.cpp:26-37), per-cell surfaces and
@@ -103,7 +165,7 @@ typedef struct mmc_world_desc {
   const double* mg_chi;             /* [n_nuclides][G_in][G_out] */
 
   /* continuous-energy tables: see mmc_ce_desc (NULL for multigroup worlds) */
-  const struct mmc_ce_desc* ce;
+  const mmc_ce_desc* ce;
 } mmc_world_desc;
 
 /* Source.cpp:131-154: constant position, constant / isotropic / isotropic-flux
@@ -232,6 +294,51 @@ int mmc_trace_histories(
  * (fn 3) -- and the libstdc++ generate_canonical stream (fn 4: x[i] is a seed,
  * out0[i] the first canonical double of std::minstd_rand{seed}).  HOST buffers. */
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n);
+
+/* Diagnostic (the reference's test_World.cpp / test_Cell.cpp / test_CSGSurface.cpp cases run through it): for each
+ * of n query points, World::FindCellContaining(position) (-1 where the reference throws) and, from that cell,
+ * Cell::NearestSurface(position, direction): surface index and distance (inf when no surface is ahead).
+ * positions / directions are [n][3]; directions are used as given (not normalised).  HOST buffers. */
+int mmc_test_geometry(const mmc_world* world, size_t n, const double* positions, const double* directions,
+                      int32_t* cell, int32_t* surface, double* distance);
+
+/* ---- host layer ---------------------------------------------------------------
+ * The C++17 host (minimc_b200/host: XML deck -> World/Material/Nuclide/Source/
+ * EstimatorSet -> Driver) behind C entry points, for callers that are not C++
+ * (the Python tests, bench.py).  A C++ caller uses minimc_b200/host/minimc.hpp
+ * directly: `minimc::Driver::Create(path)->Solve()` is the reference's own
+ * call sequence (minimc.cpp:16-21). */
+typedef struct mmc_driver mmc_driver;
+
+/* Driver::Create(path) (Driver.cpp:19-35).  Construction errors carry the
+ * reference's messages (mmc_last_error). */
+int mmc_driver_create(const char* xml_path, mmc_driver** out);
+int mmc_driver_create_from_string(const char* xml_text, mmc_driver** out);
+void mmc_driver_destroy(mmc_driver* driver);
+/* Knobs of the GPU path; tracking in `options` is ignored (the deck decides). */
+int mmc_driver_set_options(mmc_driver* driver, const mmc_run_options* options);
+/* This process transports histories [rank*N/P, (rank+1)*N/P) of the batch. */
+int mmc_driver_set_shard(mmc_driver* driver, int32_t rank, int32_t world_size);
+/* Driver::Solve() (Driver.hpp:30): runs on the GPU, keeps the EstimatorSet. */
+int mmc_driver_solve(mmc_driver* driver);
+uint64_t mmc_driver_batchsize(const mmc_driver* driver);
+uint64_t mmc_driver_total_bins(const mmc_driver* driver);
+/* Concatenated Scorable::scores / square_scores of the last Solve(). */
+int mmc_driver_scores(const mmc_driver* driver, double* scores, double* square_scores, uint64_t n);
+/* EstimatorSet::operator+= with another rank's scores (Estimator.cpp:215-231). */
+int mmc_driver_add_scores(mmc_driver* driver, const double* scores, const double* square_scores, uint64_t n);
+int mmc_driver_counters(const mmc_driver* driver, mmc_counters* counters);
+/* The text runminimc writes to <input>.out: "<batchsize>\n" + EstimatorSet::to_string()
+ * (minimc.cpp:20-21).  Returns the full length; copies at most cap-1 bytes. */
+size_t mmc_driver_output(const mmc_driver* driver, char* buf, size_t cap);
+/* The flattened World as JSON with C99 hex floats (test hook). */
+size_t mmc_driver_world_json(const mmc_driver* driver, char* buf, size_t cap);
+/* Parity hook: mmc_trace_histories for histories [first, first + n) of a fixed-source deck. */
+int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
+                     size_t cap, size_t* n_records);
+/* k-eigenvalue results of the last Solve(): mean and standard deviation of the
+ * mean over active cycles, and k of every cycle (inactive first). */
+int mmc_driver_keff(const mmc_driver* driver, double* k_mean, double* k_std, double* k_cycle, size_t cap, size_t* n_cycles);
 
 #ifdef __cplusplus
 }

@@ -98,7 +98,12 @@ class RunOptions(C.Structure):
 EXPORTS = (
     "mmc_abi_version", "mmc_last_error", "mmc_device_count", "mmc_world_create", "mmc_world_destroy",
     "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_device", "mmc_trace_histories",
-    "mmc_test_device_math",
+    "mmc_test_device_math", "mmc_test_geometry",
+    # host layer
+    "mmc_driver_create", "mmc_driver_create_from_string", "mmc_driver_destroy", "mmc_driver_set_options",
+    "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
+    "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
+    "mmc_driver_trace",
 )
 
 _lib = None
@@ -143,6 +148,39 @@ def load() -> C.CDLL:
         C.POINTER(EventRecord), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mmc_test_device_math.restype = C.c_int
     lib.mmc_test_device_math.argtypes = [C.c_int, _pd, _pd, _pd, C.c_size_t]
+    lib.mmc_test_geometry.restype = C.c_int
+    lib.mmc_test_geometry.argtypes = [C.c_void_p, C.c_size_t, _pd, _pd, _pi, _pi, _pd]
+    lib.mmc_driver_create.restype = C.c_int
+    lib.mmc_driver_create.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.mmc_driver_create_from_string.restype = C.c_int
+    lib.mmc_driver_create_from_string.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.mmc_driver_destroy.restype = None
+    lib.mmc_driver_destroy.argtypes = [C.c_void_p]
+    lib.mmc_driver_set_options.restype = C.c_int
+    lib.mmc_driver_set_options.argtypes = [C.c_void_p, C.POINTER(RunOptions)]
+    lib.mmc_driver_set_shard.restype = C.c_int
+    lib.mmc_driver_set_shard.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.mmc_driver_solve.restype = C.c_int
+    lib.mmc_driver_solve.argtypes = [C.c_void_p]
+    lib.mmc_driver_batchsize.restype = C.c_uint64
+    lib.mmc_driver_batchsize.argtypes = [C.c_void_p]
+    lib.mmc_driver_total_bins.restype = C.c_uint64
+    lib.mmc_driver_total_bins.argtypes = [C.c_void_p]
+    lib.mmc_driver_scores.restype = C.c_int
+    lib.mmc_driver_scores.argtypes = [C.c_void_p, _pd, _pd, C.c_uint64]
+    lib.mmc_driver_add_scores.restype = C.c_int
+    lib.mmc_driver_add_scores.argtypes = [C.c_void_p, _pd, _pd, C.c_uint64]
+    lib.mmc_driver_counters.restype = C.c_int
+    lib.mmc_driver_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    lib.mmc_driver_output.restype = C.c_size_t
+    lib.mmc_driver_output.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.mmc_driver_world_json.restype = C.c_size_t
+    lib.mmc_driver_world_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.mmc_driver_trace.restype = C.c_int
+    lib.mmc_driver_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(EventRecord), C.c_size_t,
+                                     C.POINTER(C.c_size_t)]
+    lib.mmc_driver_keff.restype = C.c_int
+    lib.mmc_driver_keff.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t)]
     if lib.mmc_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mmc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -327,6 +365,15 @@ class World:
             self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
             C.byref(o), d_scores, d_square, d_counters))
 
+    def geometry(self, positions, directions):
+        """mmc_test_geometry: (cell, nearest surface, distance) per query point, evaluated on the GPU."""
+        pos, dirs = _arr(positions, np.float64).reshape(-1, 3), _arr(directions, np.float64).reshape(-1, 3)
+        n = len(pos)
+        cell, surface, distance = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        check(load().mmc_test_geometry(self._handle, n, _ptr(pos, C.c_double), _ptr(dirs, C.c_double),
+                                       _ptr(cell, C.c_int32), _ptr(surface, C.c_int32), _ptr(distance, C.c_double)))
+        return cell, surface, distance
+
     def trace(self, source, seed0, first_history, n_histories, *, tracking=TRACK_SURFACE, cap=1 << 16):
         records = (EventRecord * cap)()
         n = C.c_size_t()
@@ -334,3 +381,97 @@ class World:
         check(load().mmc_trace_histories(
             self._handle, C.byref(source), seed0, first_history, n_histories, C.byref(o), records, cap, C.byref(n)))
         return [records[i] for i in range(n.value)]
+
+
+class Driver:
+    """The C++ host's Driver (minimc_b200/host/minimc.hpp) through the C entry points: parses an XML deck exactly
+    as the reference's Driver::Create does, and Solve() runs the batch on the GPU."""
+
+    def __init__(self, path=None, *, text=None):
+        self._handle = C.c_void_p()
+        if text is not None:
+            check(load().mmc_driver_create_from_string(text.encode(), C.byref(self._handle)))
+        else:
+            check(load().mmc_driver_create(os.fspath(path).encode(), C.byref(self._handle)))
+
+    def close(self):
+        if self._handle:
+            load().mmc_driver_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def batchsize(self) -> int:
+        return int(load().mmc_driver_batchsize(self._handle))
+
+    @property
+    def total_bins(self) -> int:
+        return int(load().mmc_driver_total_bins(self._handle))
+
+    def set_options(self, *, device=-1, secondary_capacity=0, pending_capacity=0, blocks_per_sm=0, rng_mode=RNG_MINSTD_COMPAT):
+        o = RunOptions()
+        o.struct_size = C.sizeof(RunOptions)
+        o.device = device
+        o.rng_mode = rng_mode
+        o.secondary_capacity = secondary_capacity
+        o.pending_capacity = pending_capacity
+        o.blocks_per_sm = blocks_per_sm
+        check(load().mmc_driver_set_options(self._handle, C.byref(o)))
+
+    def set_shard(self, rank: int, world_size: int):
+        check(load().mmc_driver_set_shard(self._handle, rank, world_size))
+
+    def solve(self):
+        check(load().mmc_driver_solve(self._handle))
+        return self.scores()
+
+    def scores(self):
+        n = self.total_bins
+        scores, squares = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        check(load().mmc_driver_scores(self._handle, _ptr(scores, C.c_double), _ptr(squares, C.c_double), n))
+        return scores[:n], squares[:n]
+
+    def add_scores(self, scores, squares):
+        scores, squares = _arr(scores, np.float64), _arr(squares, np.float64)
+        check(load().mmc_driver_add_scores(self._handle, _ptr(scores, C.c_double), _ptr(squares, C.c_double), scores.size))
+
+    def counters(self) -> dict:
+        c = Counters()
+        check(load().mmc_driver_counters(self._handle, C.byref(c)))
+        return c.as_dict()
+
+    def _text(self, fn) -> str:
+        n = fn(self._handle, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        fn(self._handle, buf, n + 1)
+        return buf.value.decode()
+
+    def output(self) -> str:
+        """The text of <input>.out (minimc.cpp:20-21)."""
+        return self._text(load().mmc_driver_output)
+
+    def world_json(self) -> dict:
+        import json
+        text = self._text(load().mmc_driver_world_json)
+        if not text:
+            raise MinimcError(ERR_INVALID, last_error())
+        return json.loads(text)
+
+    def trace(self, first_history: int, n_histories: int, cap=1 << 18):
+        records = (EventRecord * cap)()
+        n = C.c_size_t()
+        check(load().mmc_driver_trace(self._handle, first_history, n_histories, records, cap, C.byref(n)))
+        return [records[i] for i in range(n.value)]
+
+    def keff(self):
+        k_mean, k_std, n = C.c_double(), C.c_double(), C.c_size_t()
+        check(load().mmc_driver_keff(self._handle, C.byref(k_mean), C.byref(k_std), None, 0, C.byref(n)))
+        cycles = np.zeros(max(n.value, 1))
+        check(load().mmc_driver_keff(self._handle, C.byref(k_mean), C.byref(k_std), _ptr(cycles, C.c_double), n.value,
+                                     C.byref(n)))
+        return k_mean.value, k_std.value, cycles[:n.value]

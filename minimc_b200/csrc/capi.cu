@@ -58,6 +58,14 @@ public:
 
 }  // namespace
 
+namespace mmc {
+// used by the host layer (minimc_b200/host/host_capi.cpp) to report C++ exceptions
+int set_last_error(int status, const std::string& message) {
+  g_error = message;
+  return status;
+}
+}  // namespace mmc
+
 struct mmc_world {
   int device = 0;
   char* d_blob = nullptr;
@@ -79,13 +87,68 @@ struct mmc_world {
 
 namespace {
 
+int validate_table(const mmc_table1d& t, const char* what, int nuclide, bool required) {
+  if (t.n == 0 && !required) return MMC_OK;
+  if (t.n == 0 || !t.x || !t.y) return fail(MMC_ERR_INVALID, "nuclide %d: %s table is empty", nuclide, what);
+  if (t.n > 0x7fffffffull) return fail(MMC_ERR_INVALID, "nuclide %d: %s table too large", nuclide, what);
+  for (uint64_t i = 1; i < t.n; i++)
+    if (!(t.x[i] > t.x[i - 1])) return fail(MMC_ERR_INVALID, "nuclide %d: %s table keys must be strictly increasing", nuclide, what);
+  return MMC_OK;
+}
+
+int validate_partitions(const mmc_tsl_partition* p, int n, const char* what, int nuclide) {
+  if (n < 1 || !p) return fail(MMC_ERR_INVALID, "nuclide %d: thermal scattering data without %s partitions", nuclide, what);
+  double previous = 0;
+  for (int i = 0; i < n; i++) {
+    const mmc_tsl_partition& q = p[i];
+    if (!q.n_cdf || !q.n_grid || !q.n_temperature || !q.rank || !q.cdf || !q.grid || !q.temperature || !q.cdf_modes ||
+        !q.singular_values || !q.grid_T_modes)
+      return fail(MMC_ERR_INVALID, "nuclide %d: %s partition %d has an empty table", nuclide, what, i);
+    for (uint64_t k = 0; k < q.n_grid; k++) {
+      // the reference asserts this ordering (ThermalScattering.cpp:46-51,79-84)
+      if (!(previous < q.grid[k])) return fail(MMC_ERR_INVALID, "nuclide %d: %s partition grids must be increasing", nuclide, what);
+      previous = q.grid[k];
+    }
+  }
+  return MMC_OK;
+}
+
+int validate_ce(const mmc_world_desc* d) {
+  for (int n = 0; n < d->n_nuclides; n++) {
+    const mmc_ce_nuclide& c = d->ce->nuclides[n];
+    if (int s = validate_table(c.total, "total", n, true)) return s;
+    if (c.n_reactions < 0 || c.n_reactions > kMaxCeReactions || (c.n_reactions && !c.reactions))
+      return fail(MMC_ERR_INVALID, "nuclide %d: %d reactions (at most %d supported)", n, c.n_reactions, kMaxCeReactions);
+    for (int r = 0; r < c.n_reactions; r++) {
+      const mmc_ce_reaction& x = c.reactions[r];
+      if (x.kind != MMC_REACTION_CAPTURE && x.kind != MMC_REACTION_SCATTER && x.kind != MMC_REACTION_FISSION)
+        return fail(MMC_ERR_INVALID, "nuclide %d reaction %d: unknown kind %d", n, r, x.kind);
+      if (int s = validate_table(x.xs, "reaction", n, true)) return s;
+      if (x.has_nubar)
+        if (int s = validate_table(x.nubar, "nubar", n, true)) return s;
+      if (x.tsl) {
+        const mmc_tsl_desc& t = *x.tsl;
+        if (x.kind != MMC_REACTION_SCATTER) return fail(MMC_ERR_INVALID, "nuclide %d: only scatter may carry thermal scattering data", n);
+        if (int s = validate_table(t.majorant, "tsl majorant", n, true)) return s;
+        if (!t.n_energy || !t.n_temperature || !t.rank || !t.energy || !t.temperature || !t.xs_E || !t.xs_S || !t.xs_T)
+          return fail(MMC_ERR_INVALID, "nuclide %d: empty thermal scattering cross-section tables", n);
+        if (int s = validate_partitions(t.beta_partitions, t.n_beta_partitions, "beta", n)) return s;
+        if (int s = validate_partitions(t.alpha_partitions, t.n_alpha_partitions, "alpha", n)) return s;
+      }
+    }
+  }
+  return MMC_OK;
+}
+
 int validate_world(const mmc_world_desc* d) {
   if (!d) return fail(MMC_ERR_INVALID, "world desc is NULL");
   if (d->struct_size != sizeof(mmc_world_desc) || d->abi_version != MMC_ABI_VERSION)
     return fail(MMC_ERR_INVALID, "mmc_world_desc ABI mismatch: struct_size %u (expected %zu), abi_version %u (expected %d)",
                 d->struct_size, sizeof(mmc_world_desc), d->abi_version, MMC_ABI_VERSION);
   if (d->n_surfaces < 1 || d->n_cells < 1) return fail(MMC_ERR_INVALID, "world needs at least one surface and one cell");
-  if (d->n_groups < 1) return fail(MMC_ERR_INVALID, "continuous-energy worlds are not supported by this build (n_groups = %d)", d->n_groups);
+  if (d->n_groups < 0) return fail(MMC_ERR_INVALID, "n_groups = %d", d->n_groups);
+  if (d->n_groups == 0 && d->n_nuclides > 0 && (!d->ce || !d->ce->nuclides))
+    return fail(MMC_ERR_INVALID, "continuous-energy world (n_groups = 0) without mmc_ce_desc tables");
   if (d->n_materials < 0 || d->n_nuclides < 0) return fail(MMC_ERR_INVALID, "negative table size");
   if (!d->surface_type || !d->surface_param || !d->cell_material || !d->cell_surface_begin || !d->cell_surface_index ||
       !d->cell_surface_sense)
@@ -115,6 +178,7 @@ int validate_world(const mmc_world_desc* d) {
           return fail(MMC_ERR_INVALID, "material %d: nuclide index %d out of range", m, d->material_nuclide_index[k]);
     }
   }
+  if (d->n_groups == 0) return validate_ce(d);
   if (d->n_nuclides > 0 &&
       (!d->mg_reaction_mask || !d->mg_total || !d->mg_capture || !d->mg_scatter || !d->mg_fission || !d->mg_nubar ||
        !d->mg_scatter_probs || !d->mg_chi))
@@ -227,9 +291,12 @@ int prepare_run(
   } else if (source->direction_kind != MMC_DIR_ISOTROPIC) {
     return fail(MMC_ERR_INVALID, "unknown source direction kind %d", source->direction_kind);
   }
-  if (source->group < 1 || source->group > static_cast<uint64_t>(w->header.n_groups))
+  const bool continuous_energy = w->header.n_groups == 0;
+  if (!continuous_energy && (source->group < 1 || source->group > static_cast<uint64_t>(w->header.n_groups)))
     return fail(MMC_ERR_INVALID, "source group %llu outside 1..%d", static_cast<unsigned long long>(source->group),
                 w->header.n_groups);
+  if (continuous_energy && !(source->energy > 0)) return fail(MMC_ERR_INVALID, "source energy must be positive (MeV)");
+  run.continuous_energy = continuous_energy ? 1 : 0;
   run.source.group = source->group;
   run.source.energy = source->energy;
   // estimators
@@ -264,9 +331,10 @@ int prepare_run(
   run.pending_capacity = opt.pending_capacity ? opt.pending_capacity : 32;
   if (n_estimators == 0) run.pending_capacity = 1;
   run.world_bytes = w->blob_bytes;
-  run.world_in_smem = (!trace && w->blob_bytes <= 96 * 1024) ? 1 : 0;
+  // continuous-energy tables are read through the read-only global path (L2-resident)
+  run.world_in_smem = (!trace && !continuous_energy && w->blob_bytes <= 96 * 1024) ? 1 : 0;
   // launch shape
-  int per_sm = max_blocks_per_sm(run.tracking, run.world_in_smem ? run.world_bytes : 0);
+  int per_sm = max_blocks_per_sm(run.tracking, continuous_energy, run.world_in_smem ? run.world_bytes : 0);
   if (per_sm < 1) per_sm = 1;
   if (opt.blocks_per_sm && static_cast<int>(opt.blocks_per_sm) < per_sm) per_sm = opt.blocks_per_sm;
   long long blocks = static_cast<long long>(w->sm_count) * per_sm;
@@ -366,7 +434,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   h.off_mat_nuc_index = b.add(d->material_nuclide_index, nnz_mat);
   h.off_mat_nuc_afrac = b.add(d->material_nuclide_afrac, nnz_mat);
   const size_t ng = static_cast<size_t>(d->n_nuclides) * G;
-  h.off_mg_mask = b.add(d->mg_reaction_mask, d->n_nuclides);
+  h.off_mg_mask = b.add(d->mg_reaction_mask, G > 0 ? d->n_nuclides : 0);
   h.off_mg_total = b.add(d->mg_total, ng);
   h.off_mg_capture = b.add(d->mg_capture, ng);
   h.off_mg_scatter = b.add(d->mg_scatter, ng);
@@ -374,7 +442,87 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   h.off_mg_nubar = b.add(d->mg_nubar, ng);
   h.off_mg_scatter_probs = b.add(d->mg_scatter_probs, ng * G);
   h.off_mg_chi = b.add(d->mg_chi, ng * G);
+  bool has_fission = false;
+  for (int n = 0; G > 0 && n < d->n_nuclides; n++) has_fission = has_fission || (d->mg_reaction_mask[n] & MMC_REACTION_FISSION);
+  if (G == 0 && d->n_nuclides > 0) {
+    auto table = [&b](const mmc_table1d& t) {
+      Table1D out{};
+      out.n = static_cast<uint32_t>(t.n);
+      if (t.n) {
+        out.off_x = b.add(t.x, t.n);
+        out.off_y = b.add(t.y, t.n);
+      }
+      return out;
+    };
+    auto partitions = [&b](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
+      std::vector<TslPartition> out(n);
+      for (int i = 0; i < n; i++) {
+        const mmc_tsl_partition& q = p[i];
+        TslPartition& o = out[i];
+        o.n_cdf = static_cast<uint32_t>(q.n_cdf);
+        o.n_grid = static_cast<uint32_t>(q.n_grid);
+        o.n_T = static_cast<uint32_t>(q.n_temperature);
+        o.rank = static_cast<uint32_t>(q.rank);
+        o.off_cdf = b.add(q.cdf, q.n_cdf);
+        o.off_T = b.add(q.temperature, q.n_temperature);
+        o.off_cdf_modes = b.add(q.cdf_modes, q.n_cdf * q.rank);
+        o.off_S = b.add(q.singular_values, q.rank);
+        o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
+        o.grid_begin = static_cast<uint32_t>(concatenated.size());
+        concatenated.insert(concatenated.end(), q.grid, q.grid + q.n_grid);
+      }
+      return b.add(out.data(), out.size());
+    };
+    std::vector<CeNuclide> nuclides(d->n_nuclides);
+    for (int n = 0; n < d->n_nuclides; n++) {
+      const mmc_ce_nuclide& c = d->ce->nuclides[n];
+      CeNuclide& o = nuclides[n];
+      o = CeNuclide{};
+      o.awr = c.awr;
+      o.total = table(c.total);
+      o.total_temperature = c.total_temperature;
+      o.n_reactions = c.n_reactions;
+      for (int r = 0; r < c.n_reactions; r++) {
+        const mmc_ce_reaction& x = c.reactions[r];
+        CeReaction& xr = o.reactions[r];
+        xr.kind = x.kind;
+        xr.xs = table(x.xs);
+        xr.temperature = x.temperature;
+        if (x.has_nubar) xr.nubar = table(x.nubar);
+        has_fission = has_fission || x.kind == MMC_REACTION_FISSION;
+        if (x.tsl) {
+          const mmc_tsl_desc& t = *x.tsl;
+          TslTable tt{};
+          tt.majorant = table(t.majorant);
+          tt.n_E = static_cast<uint32_t>(t.n_energy);
+          tt.n_T = static_cast<uint32_t>(t.n_temperature);
+          tt.rank = static_cast<uint32_t>(t.rank);
+          tt.off_E = b.add(t.energy, t.n_energy);
+          tt.off_T = b.add(t.temperature, t.n_temperature);
+          tt.off_xs_E = b.add(t.xs_E, t.n_energy * t.rank);
+          tt.off_xs_S = b.add(t.xs_S, t.rank);
+          tt.off_xs_T = b.add(t.xs_T, t.n_temperature * t.rank);
+          std::vector<double> Es, betas;
+          tt.n_beta_partitions = t.n_beta_partitions;
+          tt.off_beta_partitions = partitions(t.beta_partitions, t.n_beta_partitions, Es);
+          tt.n_alpha_partitions = t.n_alpha_partitions;
+          tt.off_alpha_partitions = partitions(t.alpha_partitions, t.n_alpha_partitions, betas);
+          tt.n_Es = static_cast<uint32_t>(Es.size());
+          tt.off_Es = b.add(Es.data(), Es.size());
+          tt.n_betas = static_cast<uint32_t>(betas.size());
+          tt.off_betas = b.add(betas.data(), betas.size());
+          tt.beta_cutoff = t.beta_cutoff;
+          tt.alpha_cutoff = t.alpha_cutoff;
+          tt.awr = t.awr;
+          tt.cutoff_energy = t.energy[t.n_energy - 1];  // ThermalScattering.hpp:125-126
+          xr.off_tsl = b.add(&tt, 1);
+        }
+      }
+    }
+    h.off_ce_nuclides = b.add(nuclides.data(), nuclides.size());
+  }
   b.pad();
+  if (b.bytes.size() > 0xfffffff0ull) return fail(MMC_ERR_INVALID, "world tables exceed 4 GiB");
   h.total_bytes = static_cast<uint32_t>(b.bytes.size());
   b.header() = h;
 
@@ -382,7 +530,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   w->device = device;
   w->header = h;
   w->blob_bytes = h.total_bytes;
-  for (int n = 0; n < d->n_nuclides; n++) w->has_fission = w->has_fission || (d->mg_reaction_mask[n] & MMC_REACTION_FISSION);
+  w->has_fission = has_fission;
   cudaDeviceProp prop{};
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaMalloc(&w->d_blob, w->blob_bytes);
@@ -515,6 +663,33 @@ int mmc_trace_histories(
   *n_records = static_cast<size_t>(std::min<unsigned long long>(n, cap));
   if (n > cap) return fail(MMC_ERR_CAPACITY, "trace needs %llu records but cap is %zu", n, cap);
   return status_from_counters(h_counters);
+}
+
+int mmc_test_geometry(const mmc_world* world, size_t n, const double* positions, const double* directions,
+                      int32_t* cell, int32_t* surface, double* distance) {
+  if (!world || !positions || !directions || !cell || !surface || !distance) return fail(MMC_ERR_INVALID, "bad arguments");
+  if (n == 0) return MMC_OK;
+  MMC_CUDA(cudaSetDevice(world->device));
+  double *d_pos = nullptr, *d_dir = nullptr, *d_dist = nullptr;
+  int32_t *d_cell = nullptr, *d_surf = nullptr;
+  cudaError_t e = cudaMalloc(&d_pos, 3 * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_dir, 3 * n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_dist, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cell, n * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_surf, n * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(d_pos, positions, 3 * n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_dir, directions, 3 * n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_test_geometry(world->d_blob, n, d_pos, d_dir, d_cell, d_surf, d_dist, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(cell, d_cell, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(surface, d_surf, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(distance, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_pos);
+  cudaFree(d_dir);
+  cudaFree(d_dist);
+  cudaFree(d_cell);
+  cudaFree(d_surf);
+  if (e != cudaSuccess) return fail(MMC_ERR_CUDA, "mmc_test_geometry: %s", cudaGetErrorString(e));
+  return MMC_OK;
 }
 
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n) {

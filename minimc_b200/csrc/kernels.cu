@@ -40,6 +40,7 @@ __device__ __forceinline__ void load_site(const BankSite& s, Particle& p) {
   p.dy = s.direction[1];
   p.dz = s.direction[2];
   p.group = s.energy_bits;
+  p.energy = __longlong_as_double(static_cast<long long>(s.energy_bits));
   p.rng.x = lcg_seed(s.seed);
   p.cell = -1;
   p.surface = -1;
@@ -81,7 +82,7 @@ __device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t
 
 }  // namespace
 
-template <int kTracking>
+template <int kTracking, bool kCE>
 __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
@@ -173,14 +174,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
           p.event = MMC_EV_LEAK;
         }
       }
-      if (p.cell >= 0) transport_step<kTracking>(w, p, dq, o);
+      if (p.cell >= 0) transport_step<kTracking, kCE>(w, p, dq, o);
       count_event(c, p, o);
     }
 
     // ---- EstimatorSetProxy::Score(p): TransportMethod.cpp:74
     for (int32_t e = 0; e < run.n_estimators; e++) {
       uint64_t bin = 0;
-      const bool hit = alive && !o.error_lost && estimator_score(run.estimators[e], bounds, p, bin);
+      const bool hit = alive && !o.error_lost && estimator_score<kCE>(run.estimators[e], bounds, p, bin);
       const unsigned hit_mask = __ballot_sync(kFull, hit);
       if (hit) {
         // hits of this history in this bin so far
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
 
 // Parity hook: one thread walks histories sequentially and records every event
 // in the reference's order (see mmc_trace_histories).
-template <int kTracking>
+template <int kTracking, bool kCE>
 __global__ void trace_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, BankSite* site_scratch,
     mmc_event_record* records, unsigned long long cap, unsigned long long* n_records, mmc_counters* counters) {
@@ -238,8 +239,8 @@ __global__ void trace_kernel(
       r.history = history;
       r.particle = particle;
       r.event = p.event;
-      r.group = p.group;
-      r.energy = 0.0;
+      r.group = kCE ? 0 : p.group;
+      r.energy = kCE ? p.energy : 0.0;
       r.cell = p.cell;
       r.surface = p.surface;
       r.position[0] = p.px;
@@ -269,7 +270,7 @@ __global__ void trace_kernel(
         c.lost++;
       } else {
         while (is_alive(p.event)) {
-          transport_step<kTracking>(w, p, dq, o);
+          transport_step<kTracking, kCE>(w, p, dq, o);
           count_event(c, p, o);
           emit(history, ordinal, p);
         }
@@ -310,6 +311,34 @@ __global__ void test_math_kernel(int fn, const double* x, double* out0, double* 
   }
 }
 
+__global__ void test_geometry_kernel(
+    const char* __restrict__ world_g, size_t n, const double* pos, const double* dir, int32_t* cell, int32_t* surface,
+    double* distance) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const WorldView w(world_g);
+  Particle p;
+  p.px = pos[3 * i], p.py = pos[3 * i + 1], p.pz = pos[3 * i + 2];
+  p.dx = dir[3 * i], p.dy = dir[3 * i + 1], p.dz = dir[3 * i + 2];
+  p.cell = find_cell(w, p.px, p.py, p.pz);
+  cell[i] = p.cell;
+  surface[i] = -1;
+  distance[i] = __longlong_as_double(0x7ff0000000000000ll);
+  if (p.cell >= 0) {
+    int32_t nearest;
+    distance[i] = nearest_surface(w, p, nearest);
+    surface[i] = nearest;
+  }
+}
+
+cudaError_t launch_test_geometry(
+    const char* world_d, size_t n, const double* pos_d, const double* dir_d, int32_t* cell_d, int32_t* surface_d,
+    double* distance_d, cudaStream_t stream) {
+  test_geometry_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(
+      world_d, n, pos_d, dir_d, cell_d, surface_d, distance_d);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* out1_d, size_t n, cudaStream_t stream) {
   test_math_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(fn, x_d, out0_d, out1_d, n);
   return cudaGetLastError();
@@ -330,26 +359,39 @@ cudaError_t launch_fixed_source(
         world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters);
     return cudaGetLastError();
   };
-  if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA>);
-  return go(fixed_source_kernel<MMC_TRACK_SURFACE>);
+  if (run.continuous_energy) {
+    if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true>);
+    return go(fixed_source_kernel<MMC_TRACK_SURFACE, true>);
+  }
+  if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false>);
+  return go(fixed_source_kernel<MMC_TRACK_SURFACE, false>);
 }
 
 cudaError_t launch_trace(
     const char* world_d, const RunSpec& run, BankSite* site_scratch, mmc_event_record* records, unsigned long long cap,
     unsigned long long* n_records, mmc_counters* counters, cudaStream_t stream) {
-  if (run.tracking == MMC_TRACK_CELL_DELTA)
-    trace_kernel<MMC_TRACK_CELL_DELTA><<<1, 1, 0, stream>>>(world_d, run, site_scratch, records, cap, n_records, counters);
-  else
-    trace_kernel<MMC_TRACK_SURFACE><<<1, 1, 0, stream>>>(world_d, run, site_scratch, records, cap, n_records, counters);
-  return cudaGetLastError();
+  auto go = [&](auto kernel) {
+    kernel<<<1, 1, 0, stream>>>(world_d, run, site_scratch, records, cap, n_records, counters);
+    return cudaGetLastError();
+  };
+  if (run.continuous_energy) {
+    if (run.tracking == MMC_TRACK_CELL_DELTA) return go(trace_kernel<MMC_TRACK_CELL_DELTA, true>);
+    return go(trace_kernel<MMC_TRACK_SURFACE, true>);
+  }
+  if (run.tracking == MMC_TRACK_CELL_DELTA) return go(trace_kernel<MMC_TRACK_CELL_DELTA, false>);
+  return go(trace_kernel<MMC_TRACK_SURFACE, false>);
 }
 
-int max_blocks_per_sm(int tracking, size_t smem) {
+int max_blocks_per_sm(int tracking, bool continuous_energy, size_t smem) {
   int n = 0;
-  if (tracking == MMC_TRACK_CELL_DELTA)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fixed_source_kernel<MMC_TRACK_CELL_DELTA>, kThreadsPerBlock, smem);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fixed_source_kernel<MMC_TRACK_SURFACE>, kThreadsPerBlock, smem);
+  auto query = [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreadsPerBlock, smem); };
+  if (continuous_energy) {
+    if (tracking == MMC_TRACK_CELL_DELTA) query(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true>);
+    else query(fixed_source_kernel<MMC_TRACK_SURFACE, true>);
+  } else {
+    if (tracking == MMC_TRACK_CELL_DELTA) query(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false>);
+    else query(fixed_source_kernel<MMC_TRACK_SURFACE, false>);
+  }
   return n;
 }
 

@@ -26,7 +26,11 @@ cudaError_t launch_trace(
 
 cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* out1_d, size_t n, cudaStream_t stream);
 
+cudaError_t launch_test_geometry(
+    const char* world_d, size_t n, const double* pos_d, const double* dir_d, int32_t* cell_d, int32_t* surface_d,
+    double* distance_d, cudaStream_t stream);
+
 // occupancy query for the fused kernel
-int max_blocks_per_sm(int tracking, size_t smem);
+int max_blocks_per_sm(int tracking, bool continuous_energy, size_t smem);
 
 }  // namespace mmc

@@ -72,6 +72,7 @@ struct Particle {
   double px, py, pz;
   double dx, dy, dz;
   uint64_t group;   // multigroup: 1..G
+  double energy;    // continuous energy: MeV
   Rng rng;
   int32_t cell;
   int32_t surface;  // Particle::current_surface (persists across collisions)
@@ -260,6 +261,7 @@ __device__ inline void sample_source(const SourceSpec& src, uint64_t seed, Parti
     p.dz = src.direction[2];
   }
   p.group = src.group;
+  p.energy = src.energy;
   p.rng.x = lcg_seed(rng.raw());  // Particle ctor: rng{seed}
   p.cell = -1;
   p.surface = -1;
@@ -413,9 +415,16 @@ __device__ inline void collide_multigroup(
   }
 }
 
+}  // namespace mmc
+
+#include "physics_ce.cuh"
+
+namespace mmc {
+
 // One iteration of SurfaceTracking::Transport (TransportMethod.cpp:56-75) or
-// CellDeltaTracking::Transport (TransportMethod.cpp:92-120).
-template <int kTracking>
+// CellDeltaTracking::Transport (TransportMethod.cpp:92-120).  kCE selects the
+// Continuous (true) or Multigroup (false) Interaction of the world's nuclides.
+template <int kTracking, bool kCE>
 __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out) {
   out.secondaries = 0;
   out.error_physics = out.error_capacity = out.error_lost = false;
@@ -425,8 +434,26 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
     p.event = MMC_EV_LEAK;
     return;
   }
-  const double micro = material_micro_total(w, mat, p.group);
-  const double lambda = __dmul_rn(w.at<double>(w.h->off_mat_aden)[mat], micro);
+  // GetCollisionProbabilityDensity: total (surface tracking) or majorant (cell delta tracking)
+  double micro, majorant;
+  if (kCE) {
+    bool error = false;
+    const double T = ce::cell_temperature(w, p.cell, p.px, p.py, p.pz);
+    if (kTracking == MMC_TRACK_CELL_DELTA) {
+      majorant = ce::material_majorant(w, mat, p.energy, T, ce::cell_temperature_upper(w, p.cell), error);
+      micro = 0;  // evaluated below, only when a collision is a candidate
+    } else {
+      micro = majorant = ce::material_total(w, mat, p.energy, T, error);
+    }
+    if (error) {
+      out.error_physics = true;
+      p.event = MMC_EV_CAPTURE;
+      return;
+    }
+  } else {
+    micro = majorant = material_micro_total(w, mat, p.group);  // Multigroup::GetMajorant == GetTotal
+  }
+  const double lambda = __dmul_rn(w.at<double>(w.h->off_mat_aden)[mat], majorant);
   // std::exponential_distribution: -log(1 - u) / lambda
   const double d_coll = __ddiv_rn(-glibc::log(__dsub_rn(1.0, p.rng.canonical())), lambda);
   int32_t nearest;
@@ -447,12 +474,25 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
   } else {
     bool real = true;
     if (kTracking == MMC_TRACK_CELL_DELTA) {
-      // bernoulli_distribution{total/majorant}: u < p.  Multigroup majorant == total.
-      real = p.rng.canonical() < __ddiv_rn(micro, micro);
+      // bernoulli_distribution{total / majorant}: u < p, both evaluated BEFORE the particle streams
+      if (kCE) {
+        bool error = false;
+        micro = ce::material_total(w, mat, p.energy, ce::cell_temperature(w, p.cell, p.px, p.py, p.pz), error);
+        if (error) {
+          out.error_physics = true;
+          p.event = MMC_EV_CAPTURE;
+          return;
+        }
+      }
+      real = p.rng.canonical() < __ddiv_rn(micro, majorant);
     }
     stream(p, d_coll);
-    if (real) collide_multigroup(w, p, mat, micro, dq, out);
-    else p.event = MMC_EV_VIRTUAL_COLLISION;
+    if (real) {
+      if (kCE) ce::collide_continuous(w, p, mat, dq, out);
+      else collide_multigroup(w, p, mat, micro, dq, out);
+    } else {
+      p.event = MMC_EV_VIRTUAL_COLLISION;
+    }
   }
 }
 
@@ -488,6 +528,7 @@ __device__ __forceinline__ uint64_t bins_index(const BinsSpec& b, const double* 
 
 // CurrentEstimator::GetScore (Estimator.cpp:142-151) + ParticleBins::GetIndex
 // (Bins.cpp:196-204).  Returns true and the flattened bin when the score is 1.
+template <bool kCE>
 __device__ __forceinline__ bool estimator_score(
     const EstimatorSpec& e, const double* bounds, const Particle& p, uint64_t& bin) {
   if (p.surface != e.surface || (p.event != MMC_EV_SURFACE_CROSS && p.event != MMC_EV_LEAK)) return false;
@@ -497,7 +538,8 @@ __device__ __forceinline__ bool estimator_score(
         __dadd_rn(__dmul_rn(e.direction[0], p.dx), __dmul_rn(e.direction[1], p.dy)), __dmul_rn(e.direction[2], p.dz));
     ci = bins_index(e.cosine, bounds, mu);
   }
-  const uint64_t ei = bins_index(e.energy, bounds, static_cast<double>(p.group));
+  // std::visit(VisitEnergy(), p.GetEnergy()): the energy, or the group as a double (Bins.cpp:196-204)
+  const uint64_t ei = bins_index(e.energy, bounds, kCE ? p.energy : static_cast<double>(p.group));
   bin = e.offset + e.stride * ci + ei;
   return true;
 }

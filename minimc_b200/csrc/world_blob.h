@@ -58,7 +58,60 @@ struct WorldHeader {
   uint32_t off_mg_total;        // double[n_nuclides][G]
   uint32_t off_mg_capture, off_mg_scatter, off_mg_fission, off_mg_nubar;
   uint32_t off_mg_scatter_probs, off_mg_chi;  // double[n_nuclides][G][G]
+  uint32_t off_ce_nuclides;     // CeNuclide[n_nuclides]; 0 for multigroup worlds
+};
+
+// ---- continuous-energy tables (blob offsets; see include/minimc_b200.h mmc_ce_desc)
+constexpr int kMaxCeReactions = 4;  // per nuclide: capture, scatter, fission (+1 spare)
+
+struct Table1D {
+  uint32_t n;
+  uint32_t off_x, off_y;  // double[n] each
+  uint32_t pad;
+};
+
+// ThermalScattering::BetaPartition / AlphaPartition
+struct TslPartition {
+  uint32_t n_cdf, n_grid, n_T, rank;
+  uint32_t off_cdf;        // double[n_cdf]
+  uint32_t off_T;          // double[n_T]
+  uint32_t off_cdf_modes;  // double[n_cdf][rank]
+  uint32_t off_S;          // double[rank]
+  uint32_t off_modes;      // double[n_grid][n_T][rank]
+  uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
+  uint32_t pad[2];
+};
+
+// ThermalScattering
+struct TslTable {
+  Table1D majorant;
+  uint32_t n_E, n_T, rank, pad0;
+  uint32_t off_E, off_T, off_xs_E, off_xs_S, off_xs_T;
+  uint32_t n_beta_partitions, n_alpha_partitions;
+  uint32_t off_beta_partitions, off_alpha_partitions;  // TslPartition[]
+  uint32_t n_Es, off_Es;        // concatenated incident energies of the beta partitions (ThermalScattering::Es)
+  uint32_t n_betas, off_betas;  // concatenated betas of the alpha partitions (ThermalScattering::betas)
   uint32_t pad1;
+  double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
+};
+
+// one ContinuousReaction
+struct CeReaction {
+  int32_t kind;      // MMC_REACTION_*
+  uint32_t off_tsl;  // TslTable, 0 = none
+  Table1D xs;
+  double temperature;
+  Table1D nubar;     // n == 0: absent
+};
+
+// one Continuous
+struct CeNuclide {
+  double awr;
+  Table1D total;
+  double total_temperature;
+  int32_t n_reactions;
+  uint32_t pad;
+  CeReaction reactions[kMaxCeReactions];
 };
 
 // Per-run constant block (passed by value as a kernel parameter).
@@ -76,7 +129,7 @@ struct RunSpec {
   uint32_t chunk;               // histories claimed per warp refill
   uint32_t world_bytes;         // size of the world blob (multiple of 16)
   uint32_t world_in_smem;       // 1: kernels stage the blob into shared memory
-  uint32_t pad;
+  uint32_t continuous_energy;   // 1: the world's nuclides are Continuous (n_groups == 0)
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.

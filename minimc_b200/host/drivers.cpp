@@ -1,0 +1,147 @@
+// Driver / FixedSource / KEigenvalue: the reference's batch-level seam
+// (Driver.hpp:23-30).  Solve() hands the whole batch to the GPU through the C
+// ABI; there is no host transport loop.
+#include <cmath>
+#include <stdexcept>
+
+#include "minimc.hpp"
+
+namespace minimc {
+
+namespace {
+
+[[noreturn]] void ThrowLastError(const char* where) {
+  char buf[512];
+  mmc_last_error(buf, sizeof(buf));
+  throw std::runtime_error(std::string(where) + ": " + buf);
+}
+
+mmc_tracking ParseTracking(const xml::Node& root, const World& world) {
+  // TransportMethod::Create, TransportMethod.cpp:24-46
+  const xml::Node* general = root.child("general");
+  const xml::Node* tracking = general ? general->child("tracking") : nullptr;
+  const std::string tracking_type = tracking ? tracking->text() : "";
+  if (tracking_type.empty() || tracking_type == "surface") {
+    if (!world.HasConstantTemperature())
+      throw std::runtime_error("Surface tracking with continuous global temperature not allowed");
+    return MMC_TRACK_SURFACE;
+  }
+  if (tracking_type == "cell delta") return MMC_TRACK_CELL_DELTA;
+  throw std::runtime_error(tracking->path() + ": unknown tracking type \"" + tracking_type + "\"");
+}
+
+const xml::Node& GeneralChild(const xml::Node& root, const char* name) {
+  const xml::Node* general = root.child("general");
+  const xml::Node* node = general ? general->child(name) : nullptr;
+  if (!node) throw std::runtime_error(std::string("/minimc/general: \"") + name + "\" node not found");
+  return *node;
+}
+
+uint64_t ParseSeed(const xml::Node& root) {
+  // Driver.cpp:41-44: default seed 1
+  const xml::Node* general = root.child("general");
+  const xml::Node* seed = general ? general->child("seed") : nullptr;
+  return seed ? std::stoull(seed->text()) : 1;
+}
+
+const xml::Node& ProblemNode(const xml::Node& root, const char* name) {
+  const xml::Node* problemtype = root.child("problemtype");
+  const xml::Node* node = problemtype ? problemtype->child(name) : nullptr;
+  if (!node) throw std::runtime_error(std::string("/minimc/problemtype: \"") + name + "\" node not found");
+  return *node;
+}
+
+}  // namespace
+
+// Owns the device copy of a World.
+class DeviceWorld {
+public:
+  DeviceWorld(const World& world, int device) : flat{world} {
+    if (mmc_world_create(&flat.desc(), device, &handle) != MMC_OK) ThrowLastError("mmc_world_create");
+  }
+  ~DeviceWorld() { mmc_world_destroy(handle); }
+  DeviceWorld(const DeviceWorld&) = delete;
+  DeviceWorld& operator=(const DeviceWorld&) = delete;
+  FlatWorld flat;
+  mmc_world* handle = nullptr;
+};
+
+namespace {
+std::unique_ptr<Driver> CreateFromRoot(const xml::Node& root) {
+  // Driver::Create, Driver.cpp:19-35
+  const xml::Node* problemtype = root.child("problemtype");
+  const std::string problem_type = problemtype && problemtype->first_child() ? problemtype->first_child()->name() : "";
+  if (problem_type == "fixedsource") return std::make_unique<FixedSource>(root);
+  if (problem_type == "keigenvalue") return std::make_unique<KEigenvalue>(root);
+  throw std::runtime_error("/minimc/problemtype: expected a fixedsource or keigenvalue node");
+}
+}  // namespace
+
+std::unique_ptr<Driver> Driver::Create(const std::string& xml_filepath) {
+  const xml::Document doc = xml::Document::FromFile(xml_filepath);
+  return CreateFromRoot(doc.root());
+}
+
+std::unique_ptr<Driver> Driver::CreateFromString(const std::string& xml_text) {
+  const xml::Document doc = xml::Document::FromString(xml_text);
+  return CreateFromRoot(doc.root());
+}
+
+Driver::Driver(const xml::Node& root)
+    : world{root}, batchsize{std::stoull(GeneralChild(root, "histories").text())}, seed{ParseSeed(root)},
+      init_estimator_set{root.child("estimators"), world, static_cast<Real>(batchsize)},
+      threads{std::stoul(GeneralChild(root, "threads").text())}, tracking{ParseTracking(root, world)} {
+  if (const xml::Node* p = root.child("perturbations"); p && !p->children().empty())
+    throw std::runtime_error(p->path() + ": perturbations are not implemented on the GPU path");
+  run_options.struct_size = sizeof(mmc_run_options);
+  run_options.device = -1;
+  run_options.tracking = tracking;
+  run_options.rng_mode = MMC_RNG_MINSTD_COMPAT;
+}
+
+Driver::~Driver() noexcept {}
+
+std::shared_ptr<DeviceWorld> Driver::device_world() {
+  if (!device_world_) device_world_ = std::make_shared<DeviceWorld>(world, run_options.device);
+  return device_world_;
+}
+
+// ---------------------------------------------------------------- FixedSource
+FixedSource::FixedSource(const xml::Node& root) : Driver{root}, source{ProblemNode(root, "fixedsource")} {}
+
+EstimatorSet FixedSource::Solve() {
+  // FixedSource::Solve (FixedSource.cpp:22-36) with the worker pool replaced
+  // by one call: histories [first, first + count) of this rank.
+  EstimatorSet result = init_estimator_set;
+  const std::vector<mmc_estimator_desc> estimators = FlattenEstimators(result);
+  const uint64_t first = static_cast<uint64_t>(rank) * batchsize / static_cast<uint64_t>(world_size);
+  const uint64_t last = static_cast<uint64_t>(rank + 1) * batchsize / static_cast<uint64_t>(world_size);
+  std::vector<double> scores(result.total_bins(), 0.0), square_scores(result.total_bins(), 0.0);
+  run_options.tracking = tracking;
+  const int status = mmc_fixed_source_run(
+      device_world()->handle, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()), seed, first,
+      last - first, &run_options, scores.data(), square_scores.data(), &counters);
+  if (status != MMC_OK) ThrowLastError("mmc_fixed_source_run");
+  size_t offset = 0;
+  for (Estimator& e : result.estimators) {
+    for (size_t i = 0; i < e.scores.size(); i++) {
+      e.scores[i] += scores[offset + i];
+      e.square_scores[i] += square_scores[offset + i];
+    }
+    offset += e.scores.size();
+  }
+  return result;
+}
+
+std::vector<mmc_event_record> FixedSource::Trace(uint64_t first, uint64_t count, size_t cap) {
+  std::vector<mmc_event_record> records(cap);
+  size_t n = 0;
+  run_options.tracking = tracking;
+  const int status = mmc_trace_histories(
+      device_world()->handle, &source.desc, seed, first, count, &run_options, records.data(), cap, &n);
+  if (status != MMC_OK) ThrowLastError("mmc_trace_histories");
+  records.resize(n);
+  return records;
+}
+
+}  // namespace minimc

@@ -21,6 +21,8 @@ ROOT = HERE.parent.parent
 sys.path.insert(0, str(ROOT))
 from minimc_b200 import decks  # noqa: E402
 from oracle import port_py  # noqa: E402
+sys.path.insert(0, str(ROOT / "tests"))
+import util  # noqa: E402
 
 TRACE_HISTORIES = 48
 TRACKING = {"surface": None, "delta": "cell delta"}
@@ -46,6 +48,20 @@ def main():
             (HERE / f"{name}__{tracking}.trace").write_text(trace)
         path.write_text(deck_text(name, "surface"))
         (HERE / f"{name}.world.json").write_text(port_py.ref_dump(path))
+    # continuous-energy / thermal-scattering decks on the synthetic "small" tables (minimc_b200/ce_decks.py); the
+    # table files are regenerated bit-identically wherever the tests run, so absolute paths are rewritten to @TABLES@
+    from minimc_b200 import ce_decks
+    tables = tmp / "tables"
+    ce_decks.generate_tables(tables, "small")
+    (HERE / "ce").mkdir(exist_ok=True)
+    for name, tracking, text in util.ce_cases(tables):
+        path = tmp / f"ce_{name}.xml"
+        path.write_text(text)
+        out, _ = port_py.ref_run(path)
+        (HERE / "ce" / f"{name}__{tracking}.out").write_text(out)
+        trace = subprocess.run([os.fspath(port_py.REF_HARNESS), "trace", os.fspath(path), "0", str(util.CE_TRACE_HISTORIES)],
+                               capture_output=True, text=True, check=True).stdout
+        (HERE / "ce" / f"{name}__{tracking}.trace").write_text(trace)
     rng = {}
     for seed in (1, 0, 2147483647, 2147483648, 12345, 4294967297):
         lines = subprocess.run([os.fspath(port_py.REF_HARNESS), "rng", str(seed), "8"], capture_output=True, text=True,

@@ -1,0 +1,134 @@
+"""Continuous-energy + thermal-scattering parity of the CUDA path (through the C++ host's Driver and the C ABI) with
+the reference's own code: golden traces / .out files written by oracle/_ref/ref_harness (tests/golden/generate.py)
+on the synthetic tables of minimc_b200/ce_decks.py, and -- when the prebuilt reference binary travelled with the
+repo -- the reference itself on fresh seeds.
+
+Contract: for every deck in util.CE_EXACT the event sequence, energies, positions, directions and RNG states are
+BIT-EXACT and the .out text is identical; free_gas_sphere with surface tracking evaluates erf/exp (CUDA's, not
+glibc's) in the free-gas cross-section adjustment, so there the integer fields must match and floating-point fields
+agree to 1e-12 relative; its tallies agree within 3 sigma (north_star's stated tolerance)."""
+import numpy as np
+import pytest
+
+import util
+from minimc_b200 import capi, ce_decks
+from oracle import port_py
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tables(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tables")
+    ce_decks.generate_tables(d, "small")
+    return d
+
+
+def _case(tables, name, tag, **kw):
+    for n, t, text in util.ce_cases(tables, **kw):
+        if (n, t) == (name, tag):
+            return text
+    raise KeyError((name, tag))
+
+
+def _compare_traces(mine, ref, exact):
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        ta = (int(a.history), int(a.particle), int(a.event), int(a.cell), int(a.surface), int(a.rng_state))
+        tb = (b["history"], b["particle"], b["event"], b["cell"], b["surface"], b["rng_state"])
+        if a.event == 0:  # the cell of a birth record is not part of the contract
+            ta, tb = ta[:3] + ta[4:], tb[:3] + tb[4:]
+        assert ta == tb
+        va = np.array(list(a.position) + list(a.direction) + [a.energy])
+        vb = np.array(list(b["position"]) + list(b["direction"]) + [b["energy"]])
+        if exact:
+            assert np.array_equal(va, vb), (ta, va, vb)
+        else:
+            assert np.allclose(va, vb, rtol=1e-12, atol=1e-13), (ta, va, vb)
+
+
+@pytest.mark.parametrize("name,tag", util.CE_CASE_IDS)
+def test_ce_event_traces_match_reference_golden(tables, name, tag):
+    drv = capi.Driver(text=_case(tables, name, tag))
+    drv.set_options(secondary_capacity=256)
+    mine = drv.trace(0, util.CE_TRACE_HISTORIES, cap=1 << 18)
+    ref = port_py.parse_trace((util.GOLDEN / "ce" / f"{name}__{tag}.trace").read_text())
+    _compare_traces(mine, ref, (name, tag) in util.CE_EXACT)
+
+
+@pytest.mark.parametrize("name,tag", util.CE_CASE_IDS)
+def test_ce_tallies_match_reference_out(tables, name, tag):
+    drv = capi.Driver(text=_case(tables, name, tag))
+    drv.set_options(secondary_capacity=256)
+    scores, squares = drv.solve()
+    c = drv.counters()
+    assert c["n_histories"] == util.CE_HISTORIES and c["n_lost"] == 0 and c["n_physics_errors"] == 0
+    golden = (util.GOLDEN / "ce" / f"{name}__{tag}.out").read_text()
+    if (name, tag) in util.CE_EXACT:
+        assert drv.output() == golden  # the whole .out text, byte for byte
+    else:
+        _, ref = port_py.parse_out(golden)
+        _, mine = port_py.parse_out(drv.output())
+        n = util.CE_HISTORIES
+        for est in ref:
+            m, r = np.array(mine[est]["mean"], float), np.array(ref[est]["mean"], float)
+            s = np.sqrt(np.array(mine[est]["std dev"], float) ** 2 + np.array(ref[est]["std dev"], float) ** 2)
+            assert np.all(np.abs(m - r) <= 3 * s + 1.0 / n), est
+
+
+@pytest.mark.parametrize("name,tag", util.CE_CASE_IDS)
+def test_ce_fresh_seed_against_live_reference(tables, tmp_path, name, tag):
+    """The reference binary itself (prebuilt in oracle/_ref, no /root/reference needed) on a seed no fixture holds."""
+    if not port_py.ref_available():
+        pytest.skip("oracle/_ref/ref_harness was not built")
+    text = _case(tables, name, tag, histories=3000, seed=424242)
+    path = tmp_path / "deck.xml"
+    path.write_text(text)
+    drv = capi.Driver(path)
+    drv.set_options(secondary_capacity=256)
+    exact = (name, tag) in util.CE_EXACT
+    _compare_traces(drv.trace(100, 120, cap=1 << 18), port_py.ref_trace(path, 100, 120), exact)
+    drv.solve()
+    out, _ = port_py.ref_run(path)
+    if exact:
+        assert drv.output() == out
+
+
+def test_ce_full_size_tables_properties(tmp_path):
+    """The real table shapes (rank 10, partitions up to 97 x 18 x 294) at 2*10^5 histories of the
+    continuous_temperature deck (BASELINE config C5): every history ends in exactly one capture or leak, the result
+    is independent of how the batch is split across ranks, and a 3000-history prefix equals the live reference."""
+    ce_decks.generate_tables(tmp_path, "full")
+    n = 200_000
+    text = ce_decks.continuous_temperature_deck(tmp_path, histories=n, threads=4)
+    drv = capi.Driver(text=text)
+    scores, squares = drv.solve()
+    c = drv.counters()
+    assert c["n_histories"] == c["n_births"] == n
+    assert c["n_lost"] == c["n_physics_errors"] == c["n_capacity_overflow"] == 0
+    assert c["n_events"] == c["n_collisions"] + c["n_crossings"] + c["n_virtual"]
+    assert c["n_crossings"] <= n and np.all(squares == scores)  # at most one leak per history, score 1
+    total = np.zeros_like(scores)
+    for rank in range(3):
+        part = capi.Driver(text=text)
+        part.set_shard(rank, 3)
+        s, _ = part.solve()
+        total += s
+    assert np.array_equal(total, scores)
+    if port_py.ref_available():
+        path = tmp_path / "deck.xml"
+        path.write_text(ce_decks.continuous_temperature_deck(tmp_path, histories=3000, threads=4))
+        small = capi.Driver(path)
+        small.solve()
+        assert small.output() == port_py.ref_run(path)[0]
+
+
+def test_ce_resample_limit_is_reported(tables):
+    """A source far above every table (20 MeV neutron in the slab) still runs; an absurd temperature below every
+    partition's grid makes BetaPartition::Evaluate divide 0 by 0 and the resample limit trip: the reference throws
+    from a noexcept function (std::terminate); here the run reports MMC_ERR_PHYSICS."""
+    text = ce_decks.slab_deck(tables, histories=2000, temperature=100.0)
+    drv = capi.Driver(text=text)
+    with pytest.raises(capi.MinimcError) as e:
+        drv.solve()
+    assert e.value.status == capi.ERR_PHYSICS

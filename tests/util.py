@@ -113,3 +113,37 @@ def format_out_values(flat: dict, scores, squares):
         }
         off += n
     return result
+
+
+# ---------------------------------------------------------------- continuous-energy cases
+CE_TRACE_HISTORIES = 16
+CE_HISTORIES = 4000
+# decks whose every arithmetic step is restated bit for bit on the device; free_gas_sphere with surface tracking
+# reaches the free-gas cross-section adjustment (erf, exp: CUDA's, ulp-level differences) -- see physics_ce.cuh
+CE_EXACT = {("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
+            ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "delta")}
+
+
+def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
+    """(deck name, tracking tag, XML text) of every continuous-energy parity case."""
+    from minimc_b200 import ce_decks
+    cases = []
+    for name, fn in ce_decks.CE_DECKS.items():
+        for tag, tracking in TRACKING.items():
+            kw = {"histories": histories, "threads": 4, "seed": seed}
+            if name in ("single_zone", "free_gas_sphere"):
+                kw["tracking"] = tracking
+            elif name == "multi_zone":
+                kw["tracking"] = tracking or "surface"
+            elif name == "continuous_temperature":
+                if tag == "surface":
+                    continue  # cell delta tracking only (non-constant temperature)
+            elif tag == "delta":
+                continue
+            cases.append((name, tag, fn(table_dir, **kw)))
+    return cases
+
+
+CE_CASE_IDS = [("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
+               ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "surface"),
+               ("free_gas_sphere", "delta")]
