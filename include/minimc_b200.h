@@ -278,6 +278,52 @@ int mmc_fixed_source_run_device(
     int32_t n_estimators, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
     const mmc_run_options* options, uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters);
 
+/* ---- k-eigenvalue generations ----------------------------------------------------
+ * The reference's KEigenvalue::Solve is a stub (KEigenvalue.cpp:36-62: the worker launch, the fission-bank merge and
+ * the bank swap are commented out or TODO), so the power iteration is DEFINED here (DESIGN.md "k-eigenvalue") on top
+ * of the pieces the reference does have: the initial bank of KEigenvalue.cpp:29-33 and the fission physics of
+ * Multigroup::Fission / ContinuousFission::Interact.  All buffers are DEVICE buffers; calls are asynchronous on
+ * options->stream. */
+typedef struct mmc_site {           /* one banked particle, 64 bytes */
+  double position[3];
+  double direction[3];
+  uint64_t energy_bits;             /* group (multigroup) or the bits of the energy in MeV (continuous) */
+  uint32_t seed;                    /* std::minstd_rand{seed} of the particle (Particle.cpp:96-100) */
+  int32_t reserved;
+} mmc_site;
+
+/* d_bank[i] = Source::Sample(seed0 + first_index + i) kept as a site, i in [0, n)
+ * (KEigenvalue.cpp:29-33 uses seeds 1..batchsize: seed0 = 1). */
+int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_index,
+                           uint64_t n, const mmc_run_options* options, mmc_site* d_bank);
+
+/* One generation: transports the n_in particles of d_bank_in (each is one history for the tallies; scored only when
+ * `score` is non-zero -- inactive cycles do not tally).  Fission secondaries are not followed: they are written to
+ * d_bank_out in (parent index, creation ordinal) order, *d_n_out receives their number (k of the generation is
+ * n_out / n_in over all ranks).  MMC_ERR_CAPACITY is reported through d_counters->n_capacity_overflow when more than
+ * bank_capacity sites are produced. */
+int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64_t n_in,
+                       const mmc_estimator_desc* estimators, int32_t n_estimators, int32_t score,
+                       const mmc_run_options* options, mmc_site* d_bank_out, uint64_t bank_capacity, uint64_t* d_n_out,
+                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters);
+
+/* Source bank of the next generation.  The m_total fission sites of all ranks, in global order, are resampled to
+ * n_total sources with a deterministic comb: source i <- site floor(i * m_total / n_total); copies of one site get
+ * seeds site.seed + copy ordinal.  This call writes sources [first_out, first_out + n_out) into d_bank_next from
+ * d_slice, which holds global sites [slice_first, slice_first + slice_n).  *d_errors (uint64) counts sources whose
+ * site was outside the slice. */
+int mmc_bank_resample(const mmc_world* world, const mmc_site* d_slice, uint64_t slice_first, uint64_t slice_n,
+                      uint64_t m_total, uint64_t n_total, uint64_t first_out, uint64_t n_out,
+                      const mmc_run_options* options, mmc_site* d_bank_next, uint64_t* d_errors);
+
+/* Device-buffer helpers so that a host without the CUDA toolkit (the C++ host of this repo is compiled by g++) can
+ * drive the device-buffer entry points.  All synchronise with the world's stream. */
+int mmc_device_alloc(const mmc_world* world, size_t bytes, void** d_ptr);   /* zero-initialised */
+void mmc_device_free(const mmc_world* world, void* d_ptr);
+int mmc_device_zero(const mmc_world* world, void* d_ptr, size_t bytes);
+int mmc_device_read(const mmc_world* world, void* host_dst, const void* d_src, size_t bytes);
+int mmc_device_write(const mmc_world* world, void* d_dst, const void* host_src, size_t bytes);
+
 /* Parity hook (the reference has none; oracle/ref_harness.cpp obtains the same
  * records through an extra Estimator): per-event records of histories
  * [first_history, first_history+n_histories), grouped by history, particles in

@@ -99,6 +99,8 @@ EXPORTS = (
     "mmc_abi_version", "mmc_last_error", "mmc_device_count", "mmc_world_create", "mmc_world_destroy",
     "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_device", "mmc_trace_histories",
     "mmc_test_device_math", "mmc_test_geometry",
+    "mmc_source_bank_sample", "mmc_generation_run", "mmc_bank_resample",
+    "mmc_device_alloc", "mmc_device_free", "mmc_device_zero", "mmc_device_read", "mmc_device_write",
     # host layer
     "mmc_driver_create", "mmc_driver_create_from_string", "mmc_driver_destroy", "mmc_driver_set_options",
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
@@ -148,6 +150,26 @@ def load() -> C.CDLL:
         C.POINTER(EventRecord), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mmc_test_device_math.restype = C.c_int
     lib.mmc_test_device_math.argtypes = [C.c_int, _pd, _pd, _pd, C.c_size_t]
+    lib.mmc_source_bank_sample.restype = C.c_int
+    lib.mmc_source_bank_sample.argtypes = [C.c_void_p, C.POINTER(SourceDesc), C.c_uint64, C.c_uint64, C.c_uint64,
+                                           C.POINTER(RunOptions), C.c_void_p]
+    lib.mmc_generation_run.restype = C.c_int
+    lib.mmc_generation_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(EstimatorDesc), C.c_int32, C.c_int32,
+                                       C.POINTER(RunOptions), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    lib.mmc_bank_resample.restype = C.c_int
+    lib.mmc_bank_resample.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                      C.c_uint64, C.POINTER(RunOptions), C.c_void_p, C.c_void_p]
+    lib.mmc_device_alloc.restype = C.c_int
+    lib.mmc_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.mmc_device_free.restype = None
+    lib.mmc_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mmc_device_zero.restype = C.c_int
+    lib.mmc_device_zero.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.mmc_device_read.restype = C.c_int
+    lib.mmc_device_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.mmc_device_write.restype = C.c_int
+    lib.mmc_device_write.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.mmc_test_geometry.restype = C.c_int
     lib.mmc_test_geometry.argtypes = [C.c_void_p, C.c_size_t, _pd, _pd, _pi, _pi, _pd]
     lib.mmc_driver_create.restype = C.c_int
@@ -364,6 +386,27 @@ class World:
         check(load().mmc_fixed_source_run_device(
             self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
             C.byref(o), d_scores, d_square, d_counters))
+
+    SITE_BYTES = 64  # sizeof(mmc_site)
+
+    def source_bank_sample(self, source, seed0, first_index, n, d_bank, *, stream=None):
+        """mmc_source_bank_sample into a device buffer (raw pointer)."""
+        o = self._options(TRACK_SURFACE, 0, 0, 0, stream)
+        check(load().mmc_source_bank_sample(self._handle, C.byref(source), seed0, first_index, n, C.byref(o), d_bank))
+
+    def generation_run(self, d_bank_in, n_in, estimators, score, d_bank_out, bank_capacity, d_n_out, d_scores, d_square,
+                       d_counters, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0, stream=None):
+        """mmc_generation_run: raw device pointers (ints), asynchronous on `stream`."""
+        o = self._options(tracking, secondary_capacity, pending_capacity, 0, stream)
+        check(load().mmc_generation_run(
+            self._handle, d_bank_in, n_in, estimators.array, estimators.n, 1 if score else 0, C.byref(o), d_bank_out,
+            bank_capacity, d_n_out, d_scores, d_square, d_counters))
+
+    def bank_resample(self, d_slice, slice_first, slice_n, m_total, n_total, first_out, n_out, d_bank_next, d_errors, *,
+                      stream=None):
+        o = self._options(TRACK_SURFACE, 0, 0, 0, stream)
+        check(load().mmc_bank_resample(self._handle, d_slice, slice_first, slice_n, m_total, n_total, first_out, n_out,
+                                       C.byref(o), d_bank_next, d_errors))
 
     def geometry(self, positions, directions):
         """mmc_test_geometry: (cell, nearest surface, distance) per query point, evaluated on the GPU."""

@@ -83,6 +83,13 @@ struct mmc_world {
   double* d_bounds = nullptr;
   size_t bounds_bytes = 0;
   unsigned long long* d_next = nullptr;
+  // k-eigenvalue scratch
+  BankSite* d_unordered = nullptr;
+  size_t unordered_bytes = 0;
+  uint32_t* d_child_count = nullptr;
+  unsigned long long* d_child_start = nullptr;
+  unsigned long long* d_block_sums = nullptr;
+  size_t parents_capacity = 0;
 };
 
 namespace {
@@ -265,7 +272,7 @@ struct Prepared {
 int prepare_run(
     mmc_world* w, const mmc_source_desc* source, const mmc_estimator_desc* estimators, int32_t n_estimators,
     uint64_t seed0, uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, bool trace,
-    Prepared& out) {
+    Prepared& out, bool generation = false) {
   if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
   if (!source) return fail(MMC_ERR_INVALID, "source desc is NULL");
   if (n_estimators < 0 || n_estimators > kMaxEstimators)
@@ -334,7 +341,7 @@ int prepare_run(
   // continuous-energy tables are read through the read-only global path (L2-resident)
   run.world_in_smem = (!trace && !continuous_energy && w->blob_bytes <= 96 * 1024) ? 1 : 0;
   // launch shape
-  int per_sm = max_blocks_per_sm(run.tracking, continuous_energy, run.world_in_smem ? run.world_bytes : 0);
+  int per_sm = max_blocks_per_sm(run.tracking, continuous_energy, generation, run.world_in_smem ? run.world_bytes : 0);
   if (per_sm < 1) per_sm = 1;
   if (opt.blocks_per_sm && static_cast<int>(opt.blocks_per_sm) < per_sm) per_sm = opt.blocks_per_sm;
   long long blocks = static_cast<long long>(w->sm_count) * per_sm;
@@ -556,6 +563,10 @@ void mmc_world_destroy(mmc_world* w) {
   cudaFree(w->d_pending);
   cudaFree(w->d_bounds);
   cudaFree(w->d_next);
+  cudaFree(w->d_unordered);
+  cudaFree(w->d_child_count);
+  cudaFree(w->d_child_start);
+  cudaFree(w->d_block_sums);
   delete w;
 }
 
@@ -578,7 +589,101 @@ int mmc_fixed_source_run_device(
   MMC_CUDA(launch_fixed_source(
       p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
       reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,
+      nullptr, p.stream));
+  return MMC_OK;
+}
+
+static_assert(sizeof(mmc_site) == sizeof(BankSite), "mmc_site and BankSite must have the same layout");
+
+int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_index,
+                           uint64_t n, const mmc_run_options* options, mmc_site* d_bank) {
+  auto* w = const_cast<mmc_world*>(world);
+  Prepared p;
+  if (int s = prepare_run(w, source, nullptr, 0, seed0, first_index, n, options, true, p)) return s;
+  if (n && !d_bank) return fail(MMC_ERR_INVALID, "d_bank is NULL");
+  MMC_CUDA(cudaSetDevice(w->device));
+  MMC_CUDA(launch_source_bank(p.run, reinterpret_cast<BankSite*>(d_bank), p.stream));
+  return MMC_OK;
+}
+
+int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64_t n_in,
+                       const mmc_estimator_desc* estimators, int32_t n_estimators, int32_t score,
+                       const mmc_run_options* options, mmc_site* d_bank_out, uint64_t bank_capacity, uint64_t* d_n_out,
+                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters) {
+  auto* w = const_cast<mmc_world*>(world);
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  // the source of a generation is the bank: a placeholder source satisfies prepare_run's checks
+  mmc_source_desc placeholder{};
+  placeholder.direction_kind = MMC_DIR_ISOTROPIC;
+  placeholder.group = 1;
+  placeholder.energy = 1.0;
+  Prepared p;
+  if (int s = prepare_run(w, &placeholder, estimators, score ? n_estimators : 0, 0, 0, n_in, options, false, p, true)) return s;
+  if (!d_counters || !d_n_out) return fail(MMC_ERR_INVALID, "d_counters / d_n_out is NULL");
+  if (n_in && (!d_bank_in || !d_bank_out)) return fail(MMC_ERR_INVALID, "bank buffers are NULL");
+  if (p.run.total_bins && (!d_scores || !d_square_scores)) return fail(MMC_ERR_INVALID, "tally buffers are NULL");
+  MMC_CUDA(cudaSetDevice(w->device));
+  MMC_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), p.stream));
+  if (n_in == 0) return MMC_OK;
+  // every thread needs room for the secondaries of one fission
+  if (w->has_fission) p.run.secondary_capacity = std::max<uint32_t>(p.run.secondary_capacity, 16);
+  const size_t threads = static_cast<size_t>(p.cfg.blocks) * kThreadsPerBlock;
+  if (int s = ensure_scratch(w, threads, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
+  const size_t need_unordered = std::max<uint64_t>(bank_capacity, 1) * sizeof(BankSite);
+  if (need_unordered > w->unordered_bytes) {
+    cudaFree(w->d_unordered);
+    w->d_unordered = nullptr;
+    w->unordered_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_unordered, need_unordered));
+    w->unordered_bytes = need_unordered;
+  }
+  if (n_in > w->parents_capacity) {
+    cudaFree(w->d_child_count);
+    cudaFree(w->d_child_start);
+    cudaFree(w->d_block_sums);
+    w->d_child_count = nullptr;
+    w->d_child_start = nullptr;
+    w->d_block_sums = nullptr;
+    w->parents_capacity = 0;
+    MMC_CUDA(cudaMalloc(&w->d_child_count, n_in * sizeof(uint32_t)));
+    MMC_CUDA(cudaMalloc(&w->d_child_start, n_in * sizeof(unsigned long long)));
+    MMC_CUDA(cudaMalloc(&w->d_block_sums, (static_cast<size_t>(bank_scan_blocks(n_in)) + 1) * sizeof(unsigned long long)));
+    w->parents_capacity = n_in;
+  }
+  if (!p.bounds.empty())
+    MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), p.stream));
+  MMC_CUDA(cudaMemsetAsync(w->d_child_count, 0, n_in * sizeof(uint32_t), p.stream));
+  GenerationIO io;
+  io.in = reinterpret_cast<const BankSite*>(d_bank_in);
+  io.out = w->d_unordered;
+  io.capacity = bank_capacity;
+  io.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
+  io.child_count = w->d_child_count;
+  io.child_start = w->d_child_start;
+  MMC_CUDA(launch_fixed_source(
+      p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
+      reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,
+      &io, p.stream));
+  MMC_CUDA(launch_order_bank(
+      w->d_child_count, w->d_child_start, n_in, w->d_block_sums, w->d_unordered, reinterpret_cast<BankSite*>(d_bank_out),
       p.stream));
+  return MMC_OK;
+}
+
+int mmc_bank_resample(const mmc_world* world, const mmc_site* d_slice, uint64_t slice_first, uint64_t slice_n,
+                      uint64_t m_total, uint64_t n_total, uint64_t first_out, uint64_t n_out,
+                      const mmc_run_options* options, mmc_site* d_bank_next, uint64_t* d_errors) {
+  if (!world) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  if (m_total == 0 || n_total == 0) return fail(MMC_ERR_INVALID, "empty fission bank: the chain died out (m_total = 0)");
+  if (first_out + n_out > n_total) return fail(MMC_ERR_INVALID, "output range outside [0, n_total)");
+  if (n_out && (!d_slice || !d_bank_next || !d_errors)) return fail(MMC_ERR_INVALID, "bank buffers are NULL");
+  if (options && options->struct_size != sizeof(mmc_run_options)) return fail(MMC_ERR_INVALID, "mmc_run_options ABI mismatch");
+  MMC_CUDA(cudaSetDevice(world->device));
+  cudaStream_t stream = options && options->stream ? static_cast<cudaStream_t>(options->stream) : world->stream;
+  MMC_CUDA(launch_resample_bank(
+      reinterpret_cast<const BankSite*>(d_slice), slice_first, slice_n, m_total, n_total, first_out, n_out,
+      reinterpret_cast<BankSite*>(d_bank_next), reinterpret_cast<unsigned long long*>(d_errors), stream));
   return MMC_OK;
 }
 
@@ -663,6 +768,45 @@ int mmc_trace_histories(
   *n_records = static_cast<size_t>(std::min<unsigned long long>(n, cap));
   if (n > cap) return fail(MMC_ERR_CAPACITY, "trace needs %llu records but cap is %zu", n, cap);
   return status_from_counters(h_counters);
+}
+
+int mmc_device_alloc(const mmc_world* world, size_t bytes, void** d_ptr) {
+  if (!world || !d_ptr) return fail(MMC_ERR_INVALID, "world / d_ptr is NULL");
+  *d_ptr = nullptr;
+  MMC_CUDA(cudaSetDevice(world->device));
+  MMC_CUDA(cudaMalloc(d_ptr, std::max<size_t>(bytes, 1)));
+  MMC_CUDA(cudaMemsetAsync(*d_ptr, 0, std::max<size_t>(bytes, 1), world->stream));
+  MMC_CUDA(cudaStreamSynchronize(world->stream));
+  return MMC_OK;
+}
+
+void mmc_device_free(const mmc_world* world, void* d_ptr) {
+  if (!world || !d_ptr) return;
+  cudaSetDevice(world->device);
+  cudaFree(d_ptr);
+}
+
+int mmc_device_zero(const mmc_world* world, void* d_ptr, size_t bytes) {
+  if (!world || (bytes && !d_ptr)) return fail(MMC_ERR_INVALID, "world / d_ptr is NULL");
+  MMC_CUDA(cudaSetDevice(world->device));
+  MMC_CUDA(cudaMemsetAsync(d_ptr, 0, bytes, world->stream));
+  return MMC_OK;
+}
+
+int mmc_device_read(const mmc_world* world, void* host_dst, const void* d_src, size_t bytes) {
+  if (!world || (bytes && (!host_dst || !d_src))) return fail(MMC_ERR_INVALID, "bad arguments");
+  MMC_CUDA(cudaSetDevice(world->device));
+  MMC_CUDA(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, world->stream));
+  MMC_CUDA(cudaStreamSynchronize(world->stream));
+  return MMC_OK;
+}
+
+int mmc_device_write(const mmc_world* world, void* d_dst, const void* host_src, size_t bytes) {
+  if (!world || (bytes && (!d_dst || !host_src))) return fail(MMC_ERR_INVALID, "bad arguments");
+  MMC_CUDA(cudaSetDevice(world->device));
+  MMC_CUDA(cudaMemcpyAsync(d_dst, host_src, bytes, cudaMemcpyHostToDevice, world->stream));
+  MMC_CUDA(cudaStreamSynchronize(world->stream));
+  return MMC_OK;
 }
 
 int mmc_test_geometry(const mmc_world* world, size_t n, const double* positions, const double* directions,

@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_site(const BankSite& s, Particle& p) {
 
 struct ThreadCounters {
   uint32_t histories = 0, births = 0, events = 0, collisions = 0, crossings = 0, virtuals = 0, scores = 0,
-           secondaries = 0, lost = 0, capacity = 0, physics = 0;
+           secondaries = 0, banked = 0, lost = 0, capacity = 0, physics = 0;
 };
 
 __device__ __forceinline__ void count_event(ThreadCounters& c, const Particle& p, const StepOut& o) {
@@ -82,11 +82,19 @@ __device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t
 
 }  // namespace
 
-template <int kTracking, bool kCE>
+// kGeneration = false: fixed source (above).  kGeneration = true: one generation
+// of the k-eigenvalue power iteration (DESIGN.md "k-eigenvalue"): history idx
+// starts from bank.in[idx] instead of Source::Sample, and fission secondaries
+// are not followed but appended to the fission bank -- one warp-aggregated
+// atomic per warp claims the slots, each parent's run is contiguous, and
+// (count, start) per parent let order_bank_kernel restore the deterministic
+// (parent index, creation ordinal) order.
+template <int kTracking, bool kCE, bool kGeneration>
 __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
-    unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters) {
+    unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters,
+    const __grid_constant__ GenerationIO bank) {
   extern __shared__ __align__(16) char smem[];
   const WorldView w(stage_world(world_g, run.world_bytes, run.world_in_smem != 0, smem));
 
@@ -104,12 +112,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
   p.event = MMC_EV_CAPTURE;  // "dead": forces a refill
   bool done = false;         // no more work for this lane
   uint64_t w_next = 0, w_end = 0;  // warp-uniform chunk of history indices
+  uint64_t history = 0;            // index of this lane's current history
   ThreadCounters c;
 
   while (true) {
     // ---- refill: next particle of the current history, else a new history
     bool alive = is_alive(p.event);
-    if (!alive && !done && !dq.empty()) {
+    if (!kGeneration && !alive && !done && !dq.empty()) {
       // bank.back(): FixedSource.cpp:63-71
       dq.count--;
       load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
@@ -150,7 +159,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
           // scoring_proxy of the previous history is committed (incrementally);
           // a new proxy starts empty: FixedSource.cpp:48
           n_pending = 0;
-          sample_source(run.source, run.seed0 + run.first_history + idx, p);
+          history = idx;
+          if (kGeneration) load_site(bank.in[idx], p);
+          else sample_source(run.source, run.seed0 + run.first_history + idx, p);
           alive = true;
           c.histories++;
           c.births++;
@@ -176,6 +187,34 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
       }
       if (p.cell >= 0) transport_step<kTracking, kCE>(w, p, dq, o);
       count_event(c, p, o);
+    }
+    if (kGeneration) {
+      // ---- bank this event's fission secondaries (the parent is dead: it fissioned)
+      const uint32_t mine = alive ? dq.count : 0u;
+      const unsigned any = __ballot_sync(kFull, mine != 0);
+      if (any) {
+        uint32_t inclusive = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t up = __shfl_up_sync(kFull, inclusive, d);
+          if (lane >= static_cast<uint32_t>(d)) inclusive += up;
+        }
+        const uint32_t total = __shfl_sync(kFull, inclusive, 31);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(bank.n_out, static_cast<unsigned long long>(total));
+        base = __shfl_sync(kFull, base, 0);
+        if (mine) {
+          const unsigned long long start = base + (inclusive - mine);
+          if (start + mine <= bank.capacity) {
+            for (uint32_t k = 0; k < mine; k++) bank.out[start + k] = dq.slots[(dq.head + k) & dq.mask];
+            bank.child_count[history] = mine;
+            bank.child_start[history] = start;
+            c.banked += mine;
+          } else {
+            c.capacity++;
+          }
+          dq.count = 0;
+        }
+      }
     }
 
     // ---- EstimatorSetProxy::Score(p): TransportMethod.cpp:74
@@ -215,6 +254,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
   flush_counter(&counters->n_virtual, c.virtuals);
   flush_counter(&counters->n_scores, c.scores);
   flush_counter(&counters->n_secondaries, c.secondaries);
+  flush_counter(&counters->n_banked, c.banked);
   flush_counter(&counters->n_lost, c.lost);
   flush_counter(&counters->n_capacity_overflow, c.capacity);
   flush_counter(&counters->n_physics_errors, c.physics);
@@ -311,6 +351,159 @@ __global__ void test_math_kernel(int fn, const double* x, double* out0, double* 
   }
 }
 
+// ---- k-eigenvalue bank kernels -------------------------------------------------
+// Initial source bank: site i = Source::Sample(seed0 + first + i), kept as a
+// bank site (KEigenvalue.cpp:29-33 samples seeds 1..batchsize).
+__global__ void source_bank_kernel(const __grid_constant__ RunSpec run, BankSite* bank) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= run.n_histories) return;
+  Particle p;
+  sample_source(run.source, run.seed0 + run.first_history + i, p);
+  BankSite s;
+  s.position[0] = p.px, s.position[1] = p.py, s.position[2] = p.pz;
+  s.direction[0] = p.dx, s.direction[1] = p.dy, s.direction[2] = p.dz;
+  s.energy_bits = run.continuous_energy ? static_cast<uint64_t>(__double_as_longlong(p.energy)) : p.group;
+  s.seed = p.rng.x;
+  s.surface = -1;
+  bank[i] = s;
+}
+
+// Exclusive scan of child_count over the parents (three launches: block sums,
+// scan of the block sums, per-block scan + gather of each parent's run), which
+// puts the fission bank in (parent index, creation ordinal) order whatever
+// order the warps claimed their slots in.
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;  // parents per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t& block_total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inclusive = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(kFull, inclusive, d);
+    if (lane >= static_cast<uint32_t>(d)) inclusive += up;
+  }
+  if (lane == 31) smem_warp[warp] = inclusive;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < kScanThreads / 32 ? smem_warp[lane] : 0u;
+    uint32_t winc = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFull, winc, d);
+      if (lane >= static_cast<uint32_t>(d)) winc += up;
+    }
+    if (lane < kScanThreads / 32) smem_warp[lane] = winc - w;
+    if (lane == 31) smem_warp[32] = winc;
+  }
+  __syncthreads();
+  block_total = smem_warp[32];
+  return smem_warp[warp] + inclusive - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) bank_block_sums_kernel(
+    const uint32_t* __restrict__ child_count, uint64_t n_parents, unsigned long long* block_sums) {
+  __shared__ uint32_t smem_warp[33];
+  const uint64_t first = static_cast<uint64_t>(blockIdx.x) * kScanTile + threadIdx.x * kScanItems;
+  uint32_t v = 0;
+  for (int k = 0; k < kScanItems; k++)
+    if (first + k < n_parents) v += child_count[first + k];
+  uint32_t total;
+  block_exclusive_scan(v, smem_warp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) bank_scan_block_sums_kernel(unsigned long long* block_sums, uint32_t n_blocks) {
+  // one block walks the block sums in tiles (n_blocks <= n_parents / 1024)
+  __shared__ uint32_t smem_warp[33];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += kScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_blocks ? static_cast<uint32_t>(block_sums[i]) : 0u;
+    uint32_t total;
+    const uint32_t exclusive = block_exclusive_scan(v, smem_warp, total);
+    if (i < n_blocks) block_sums[i] = carry + exclusive;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) order_bank_kernel(
+    const uint32_t* __restrict__ child_count, const unsigned long long* __restrict__ child_start, uint64_t n_parents,
+    const unsigned long long* __restrict__ block_offsets, const BankSite* __restrict__ unordered, BankSite* __restrict__ ordered) {
+  __shared__ uint32_t smem_warp[33];
+  const uint64_t first = static_cast<uint64_t>(blockIdx.x) * kScanTile + threadIdx.x * kScanItems;
+  uint32_t counts[kScanItems];
+  uint32_t v = 0;
+  for (int k = 0; k < kScanItems; k++) {
+    counts[k] = first + k < n_parents ? child_count[first + k] : 0u;
+    v += counts[k];
+  }
+  uint32_t total;
+  unsigned long long dst = block_offsets[blockIdx.x] + block_exclusive_scan(v, smem_warp, total);
+  for (int k = 0; k < kScanItems; k++) {
+    if (counts[k]) {
+      const unsigned long long src = child_start[first + k];
+      for (uint32_t j = 0; j < counts[k]; j++) ordered[dst + j] = unordered[src + j];
+      dst += counts[k];
+    }
+  }
+}
+
+// Source bank of the next generation: N sites drawn from the M ordered fission
+// sites with a deterministic comb, source i <- site floor(i * M / N); copies of
+// one site get consecutive seeds (site seed + copy ordinal).
+__global__ void resample_bank_kernel(
+    const BankSite* __restrict__ slice, uint64_t slice_first, uint64_t slice_n, uint64_t m_total, uint64_t n_total,
+    uint64_t first_out, uint64_t n_out, BankSite* __restrict__ next, unsigned long long* errors) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_out) return;
+  const uint64_t i = first_out + t;
+  // floor(i * M / N) and ceil(j * N / M) with 128-bit products
+  const unsigned __int128 im = static_cast<unsigned __int128>(i) * m_total;
+  const uint64_t j = static_cast<uint64_t>(im / n_total);
+  const unsigned __int128 jn = static_cast<unsigned __int128>(j) * n_total;
+  const uint64_t i0 = static_cast<uint64_t>((jn + m_total - 1) / m_total);
+  if (j < slice_first || j >= slice_first + slice_n) {
+    atomicAdd(errors, 1ull);
+    return;
+  }
+  BankSite s = slice[j - slice_first];
+  s.seed = static_cast<uint32_t>(static_cast<uint64_t>(s.seed) + (i - i0));
+  s.surface = -1;
+  next[t] = s;
+}
+
+cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream) {
+  if (run.n_histories == 0) return cudaSuccess;
+  source_bank_kernel<<<static_cast<unsigned>((run.n_histories + 255) / 256), 256, 0, stream>>>(run, bank);
+  return cudaGetLastError();
+}
+
+uint32_t bank_scan_blocks(uint64_t n_parents) { return static_cast<uint32_t>((n_parents + kScanTile - 1) / kScanTile); }
+
+cudaError_t launch_order_bank(
+    const uint32_t* child_count, const unsigned long long* child_start, uint64_t n_parents, unsigned long long* block_sums,
+    const BankSite* unordered, BankSite* ordered, cudaStream_t stream) {
+  if (n_parents == 0) return cudaSuccess;
+  const uint32_t blocks = bank_scan_blocks(n_parents);
+  bank_block_sums_kernel<<<blocks, kScanThreads, 0, stream>>>(child_count, n_parents, block_sums);
+  bank_scan_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, blocks);
+  order_bank_kernel<<<blocks, kScanThreads, 0, stream>>>(child_count, child_start, n_parents, block_sums, unordered, ordered);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resample_bank(
+    const BankSite* slice, uint64_t slice_first, uint64_t slice_n, uint64_t m_total, uint64_t n_total, uint64_t first_out,
+    uint64_t n_out, BankSite* next, unsigned long long* errors, cudaStream_t stream) {
+  if (n_out == 0) return cudaSuccess;
+  resample_bank_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, stream>>>(
+      slice, slice_first, slice_n, m_total, n_total, first_out, n_out, next, errors);
+  return cudaGetLastError();
+}
+
 __global__ void test_geometry_kernel(
     const char* __restrict__ world_g, size_t n, const double* pos, const double* dir, int32_t* cell, int32_t* surface,
     double* distance) {
@@ -345,26 +538,41 @@ cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* 
 }
 
 // ------------------------------------------------------------------ launchers
+namespace {
+// picks the instantiation for (tracking, energy mode, fixed source | generation)
+template <typename F> auto dispatch_history_kernel(int tracking, bool ce, bool generation, F&& f) {
+  if (generation) {
+    if (ce) {
+      if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, true>);
+      return f(fixed_source_kernel<MMC_TRACK_SURFACE, true, true>);
+    }
+    if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, true>);
+    return f(fixed_source_kernel<MMC_TRACK_SURFACE, false, true>);
+  }
+  if (ce) {
+    if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, false>);
+    return f(fixed_source_kernel<MMC_TRACK_SURFACE, true, false>);
+  }
+  if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, false>);
+  return f(fixed_source_kernel<MMC_TRACK_SURFACE, false, false>);
+}
+}  // namespace
+
 cudaError_t launch_fixed_source(
     const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
     uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
-    unsigned long long* square_scores, mmc_counters* counters, cudaStream_t stream) {
+    unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream) {
   const size_t smem = run.world_in_smem ? run.world_bytes : 0;
-  auto go = [&](auto kernel) -> cudaError_t {
+  const GenerationIO io = generation ? *generation : GenerationIO{};
+  return dispatch_history_kernel(run.tracking, run.continuous_energy != 0, generation != nullptr, [&](auto kernel) -> cudaError_t {
     if (smem > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
     kernel<<<cfg.blocks, kThreadsPerBlock, smem, stream>>>(
-        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters);
+        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io);
     return cudaGetLastError();
-  };
-  if (run.continuous_energy) {
-    if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true>);
-    return go(fixed_source_kernel<MMC_TRACK_SURFACE, true>);
-  }
-  if (run.tracking == MMC_TRACK_CELL_DELTA) return go(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false>);
-  return go(fixed_source_kernel<MMC_TRACK_SURFACE, false>);
+  });
 }
 
 cudaError_t launch_trace(
@@ -382,17 +590,12 @@ cudaError_t launch_trace(
   return go(trace_kernel<MMC_TRACK_SURFACE, false>);
 }
 
-int max_blocks_per_sm(int tracking, bool continuous_energy, size_t smem) {
-  int n = 0;
-  auto query = [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreadsPerBlock, smem); };
-  if (continuous_energy) {
-    if (tracking == MMC_TRACK_CELL_DELTA) query(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true>);
-    else query(fixed_source_kernel<MMC_TRACK_SURFACE, true>);
-  } else {
-    if (tracking == MMC_TRACK_CELL_DELTA) query(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false>);
-    else query(fixed_source_kernel<MMC_TRACK_SURFACE, false>);
-  }
-  return n;
+int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem) {
+  return dispatch_history_kernel(tracking, continuous_energy, generation, [&](auto kernel) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreadsPerBlock, smem);
+    return n;
+  });
 }
 
 }  // namespace mmc

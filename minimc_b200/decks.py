@@ -249,6 +249,46 @@ def offcentre_spheres(histories=20000, threads=2, seed=None, tracking=None):
          {"name": "s1", "surface": "s1", "energy": ("linspace", 0.5, 3.5, 3)}])
 
 
+# ---------------------------------------------------------------- k-eigenvalue decks
+# None of the reference's decks is a k-eigenvalue problem and its KEigenvalue::Solve is a stub;
+# these derived decks have analytic answers (SURVEY.md 8(d) "M1k").
+def k_unity(histories=20000, threads=2, inactive=2, active=4, tracking=None):
+    """One-group infinite medium, capture 0, scatter 0.25, fission 0.75, nubar 1: every history ends in a fission
+    that yields exactly size_t(1 + U) = 1 site, so every generation banks exactly `histories` sites: k = 1 with zero
+    variance -- an exact integer-bookkeeping check of banking, ordering and resampling."""
+    return _deck(
+        _general(histories, threads, None, tracking), 1,
+        [_nuclide("fuel", scatter=[[0.25]], fission={"xs": [0.75], "nubar": [1], "chi": [[1.0]]})],
+        [_material("fuel", 1, [("fuel", 1.0)])],
+        [_sphere("sphere", "1e10")],
+        [_cell("sphere", "fuel", [("sphere", "-1")]), _cell(None, None, [("sphere", "+1")])],
+        _source(tag="keigenvalue", attrs=f'inactive="{inactive}" active="{active}"'), None)
+
+
+def k_infinite(histories=50000, threads=2, inactive=3, active=12, tracking=None):
+    """One-group infinite medium, capture 0.5, scatter 0.25, fission 0.25, nubar 2.43:
+    k_inf = nubar * Sigma_f / Sigma_a = 2.43 * 0.25 / 0.75 = 0.81."""
+    return _deck(
+        _general(histories, threads, None, tracking), 1,
+        [_nuclide("fuel", capture=[0.5], scatter=[[0.25]], fission={"xs": [0.25], "nubar": [2.43], "chi": [[1.0]]})],
+        [_material("fuel", 1, [("fuel", 1.0)])],
+        [_sphere("sphere", "1e10")],
+        [_cell("sphere", "fuel", [("sphere", "-1")]), _cell(None, None, [("sphere", "+1")])],
+        _source(tag="keigenvalue", attrs=f'inactive="{inactive}" active="{active}"'), None)
+
+
+def k_slab(histories=20000, threads=2, inactive=3, active=6, tracking=None):
+    """Two-group fuel + moderator slab with leakage (the fissile_slab geometry) as a k-eigenvalue problem with
+    `current` estimators on its faces: exercises banking in a finite geometry, both groups of chi and tallies that
+    accumulate over active cycles only."""
+    text = fissile_slab(histories=histories, threads=threads, tracking=tracking)
+    a, b = text.index("<problemtype>"), text.index("</problemtype>") + len("</problemtype>\n")
+    return text[:a] + _source(position=(0.75, 0, 0), direction="isotropic", group=1, tag="keigenvalue",
+                              attrs=f'inactive="{inactive}" active="{active}"') + text[b:]
+
+
+KDECKS = {"k_unity": k_unity, "k_infinite": k_infinite, "k_slab": k_slab}
+
 DECKS = {
     "critical": critical,
     "leakage_sphere": leakage_sphere,

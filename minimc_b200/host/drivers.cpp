@@ -10,10 +10,10 @@ namespace minimc {
 
 namespace {
 
-[[noreturn]] void ThrowLastError(const char* where) {
+[[noreturn]] void ThrowLastError(const char* where, int status) {
   char buf[512];
   mmc_last_error(buf, sizeof(buf));
-  throw std::runtime_error(std::string(where) + ": " + buf);
+  throw DeviceError(status, std::string(where) + ": " + buf);
 }
 
 mmc_tracking ParseTracking(const xml::Node& root, const World& world) {
@@ -57,7 +57,7 @@ const xml::Node& ProblemNode(const xml::Node& root, const char* name) {
 class DeviceWorld {
 public:
   DeviceWorld(const World& world, int device) : flat{world} {
-    if (mmc_world_create(&flat.desc(), device, &handle) != MMC_OK) ThrowLastError("mmc_world_create");
+    if (const int status = mmc_world_create(&flat.desc(), device, &handle)) ThrowLastError("mmc_world_create", status);
   }
   ~DeviceWorld() { mmc_world_destroy(handle); }
   DeviceWorld(const DeviceWorld&) = delete;
@@ -106,6 +106,8 @@ std::shared_ptr<DeviceWorld> Driver::device_world() {
   return device_world_;
 }
 
+const mmc_world* Driver::device_world_handle() { return device_world()->handle; }
+
 // ---------------------------------------------------------------- FixedSource
 FixedSource::FixedSource(const xml::Node& root) : Driver{root}, source{ProblemNode(root, "fixedsource")} {}
 
@@ -121,7 +123,7 @@ EstimatorSet FixedSource::Solve() {
   const int status = mmc_fixed_source_run(
       device_world()->handle, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()), seed, first,
       last - first, &run_options, scores.data(), square_scores.data(), &counters);
-  if (status != MMC_OK) ThrowLastError("mmc_fixed_source_run");
+  if (status != MMC_OK) ThrowLastError("mmc_fixed_source_run", status);
   size_t offset = 0;
   for (Estimator& e : result.estimators) {
     for (size_t i = 0; i < e.scores.size(); i++) {
@@ -139,7 +141,7 @@ std::vector<mmc_event_record> FixedSource::Trace(uint64_t first, uint64_t count,
   run_options.tracking = tracking;
   const int status = mmc_trace_histories(
       device_world()->handle, &source.desc, seed, first, count, &run_options, records.data(), cap, &n);
-  if (status != MMC_OK) ThrowLastError("mmc_trace_histories");
+  if (status != MMC_OK) ThrowLastError("mmc_trace_histories", status);
   records.resize(n);
   return records;
 }

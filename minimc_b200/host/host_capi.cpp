@@ -20,6 +20,8 @@ namespace {
 template <typename F> int Guard(F&& f) {
   try {
     return f();
+  } catch (const minimc::DeviceError& e) {
+    return mmc::set_last_error(e.status, e.what());
   } catch (const std::exception& e) {
     return mmc::set_last_error(MMC_ERR_INVALID, e.what());
   } catch (...) {
@@ -161,11 +163,11 @@ int mmc_driver_keff(const mmc_driver* driver, double* k_mean, double* k_std, dou
   if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
   const auto* k = dynamic_cast<const minimc::KEigenvalue*>(driver->driver.get());
   if (!k) return mmc::set_last_error(MMC_ERR_INVALID, "not a k-eigenvalue problem");
-  if (k_mean) *k_mean = k->result.k_mean;
-  if (k_std) *k_std = k->result.k_std;
-  if (n_cycles) *n_cycles = k->result.k_cycle.size();
+  if (k_mean) *k_mean = k->result().k_mean;
+  if (k_std) *k_std = k->result().k_std;
+  if (n_cycles) *n_cycles = k->result().k_cycle.size();
   if (k_cycle)
-    for (size_t i = 0; i < std::min(cap, k->result.k_cycle.size()); i++) k_cycle[i] = k->result.k_cycle[i];
+    for (size_t i = 0; i < std::min(cap, k->result().k_cycle.size()); i++) k_cycle[i] = k->result().k_cycle[i];
   return MMC_OK;
 }
 

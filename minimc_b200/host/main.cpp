@@ -24,7 +24,7 @@ int main(int argc, char* argv[]) {
     output_file << result.to_string();
     output_file.close();
     if (const auto* k = dynamic_cast<const minimc::KEigenvalue*>(driver.get()))
-      std::cout << "k-effective = " << k->result.k_mean << " +/- " << k->result.k_std << std::endl;
+      std::cout << "k-effective = " << k->result().k_mean << " +/- " << k->result().k_std << std::endl;
     std::cout << "Output written to " << std::filesystem::absolute(output_filepath) << std::endl;
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <memory>
 #include <optional>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,13 @@ namespace constants {
 // Constants.hpp:9-38
 constexpr Real room_temperature = 293.6;
 }  // namespace constants
+
+// A failed call into the C ABI: carries the mmc_status (lost particle, capacity, physics, CUDA ...).
+class DeviceError : public std::runtime_error {
+public:
+  DeviceError(int status, const std::string& message) : std::runtime_error(message), status(status) {}
+  const int status;
+};
 
 struct Point {
   Real x = 0, y = 0, z = 0;
@@ -271,6 +279,7 @@ public:
 
 protected:
   std::shared_ptr<DeviceWorld> device_world();
+  const mmc_world* device_world_handle();
 
 private:
   std::shared_ptr<DeviceWorld> device_world_;
@@ -295,10 +304,13 @@ public:
   explicit KEigenvalue(const xml::Node& root);
   EstimatorSet Solve() override;
   const uint64_t last_inactive, last_active;
-  KResult result;
+  const KResult& result() const { return result_; }
+  // fission-bank capacity = bank_capacity_factor * batchsize sites (k of a generation must stay below it)
+  double bank_capacity_factor = 4.0;
 
 private:
   const Source source;
+  KResult result_;
 };
 
 // Flattening of a World into the C ABI descriptor; keeps the arrays alive.

@@ -253,6 +253,8 @@ def flatten(xml_path_or_text, is_text=False):
         "threads": int(general.findtext("threads")),
         "tracking": {"surface": 0, "cell delta": 1}[tracking],
         "problemtype": problem.tag,
+        "inactive": int(problem.get("inactive", 0)),
+        "active": int(problem.get("active", 0)),
     }
 
     # Source::Source

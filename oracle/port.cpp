@@ -523,6 +523,76 @@ size_t orc_trace(
   return count;
 }
 
+// K-eigenvalue power iteration as DEFINED by this repo (DESIGN.md "k-eigenvalue";
+// the reference's KEigenvalue::Solve is a stub, KEigenvalue.cpp:36-62 -- parity
+// with the reference is therefore UNPINNED for this function; it pins the CUDA
+// path against an independent CPU statement of the same definition and against
+// analytic k-infinity).  Sequential on purpose: the definition is order-based.
+int orc_keigenvalue_run(
+    const orc_world* world, const orc_source* source, const orc_estimator* estimators, int32_t n_estimators,
+    uint64_t batchsize, uint64_t inactive, uint64_t active, int32_t tracking, double* scores, double* square_scores,
+    double* k_cycle, uint64_t* bank_sizes, orc_counters* counters) {
+  const World W{*world};
+  const Tally tally{estimators, n_estimators};
+  orc_counters cnt{};
+  Errors err;
+  struct Site {
+    Vec position, direction;
+    uint64_t group;
+    uint64_t seed;
+  };
+  // KEigenvalue.cpp:29-33: source.Sample(s), s = 1 .. batchsize
+  std::vector<Site> bank;
+  for (uint64_t s = 1; s <= batchsize; s++) {
+    const Particle p = SampleSource(*source, s);
+    bank.push_back({p.position, p.direction, p.group, p.rng.x});
+  }
+  for (uint64_t cycle = 0; cycle < inactive + active; cycle++) {
+    const bool score = cycle >= inactive;
+    std::vector<Site> fission_bank;
+    for (const Site& site : bank) {
+      Particle p;
+      p.position = site.position;
+      p.direction = site.direction;
+      p.group = site.group;
+      p.rng = MinStd{site.seed};
+      std::map<size_t, double> pending;
+      cnt.n_histories++;
+      cnt.n_births++;
+      orc_counters scratch{};
+      Transport(W, p, tracking, err, cnt, [&](const Particle& q) {
+        if (score) tally.Score(q, pending, cnt);
+        else tally.Score(q, pending, scratch);
+      });
+      if (score)
+        for (const auto& [index, s] : pending) {
+          scores[index] += s;
+          square_scores[index] += s * s;
+        }
+      for (const Particle& child : p.secondaries)  // creation order
+        fission_bank.push_back({child.position, child.direction, child.group, child.rng.x});
+    }
+    const uint64_t M = fission_bank.size(), N = batchsize;
+    k_cycle[cycle] = static_cast<double>(M) / static_cast<double>(N);
+    bank_sizes[cycle] = M;
+    if (M == 0) break;
+    // comb resampling: source i <- site floor(i * M / N); copies get seed + copy ordinal
+    std::vector<Site> next;
+    for (uint64_t i = 0; i < N; i++) {
+      const uint64_t j = static_cast<uint64_t>(static_cast<unsigned __int128>(i) * M / N);
+      const uint64_t i0 = static_cast<uint64_t>((static_cast<unsigned __int128>(j) * N + M - 1) / M);
+      Site s = fission_bank[j];
+      s.seed = static_cast<uint32_t>(s.seed + (i - i0));
+      next.push_back(s);
+    }
+    bank.swap(next);
+  }
+  cnt.n_lost = err.lost;
+  cnt.n_physics_errors = err.physics;
+  if (counters) *counters = cnt;
+  return (cnt.n_lost || cnt.n_physics_errors) ? 1 : 0;
+}
+
 void orc_rng_canonical(uint64_t seed, size_t n, double* u, uint64_t* state) {
   MinStd rng{seed};
   for (size_t i = 0; i < n; i++) {

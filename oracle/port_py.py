@@ -82,6 +82,10 @@ def load():
         lib.orc_trace.restype = C.c_size_t
         lib.orc_trace.argtypes = [C.POINTER(OrcWorld), C.POINTER(OrcSource), C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_int32, C.POINTER(OrcRecord), C.c_size_t]
+        lib.orc_keigenvalue_run.restype = C.c_int
+        lib.orc_keigenvalue_run.argtypes = [
+            C.POINTER(OrcWorld), C.POINTER(OrcSource), C.POINTER(OrcEstimator), C.c_int32, C.c_uint64, C.c_uint64,
+            C.c_uint64, C.c_int32, _pd, _pd, _pd, C.POINTER(C.c_uint64), C.POINTER(OrcCounters)]
         lib.orc_rng_canonical.restype = None
         lib.orc_rng_canonical.argtypes = [C.c_uint64, C.c_size_t, _pd, C.POINTER(C.c_uint64)]
         _lib = lib
@@ -151,6 +155,25 @@ class Problem:
             C.byref(self.world), C.byref(self.source), self.estimators, self.n_estimators, seed0, first, n, tracking,
             threads, scores.ctypes.data_as(_pd), squares.ctypes.data_as(_pd), C.byref(counters))
         return scores[:self.total_bins], squares[:self.total_bins], counters.as_dict(), status
+
+    def keigenvalue(self, batchsize=None, inactive=None, active=None, tracking=None):
+        """The power iteration of DESIGN.md "k-eigenvalue" on the CPU: (scores, squares, k per cycle, bank sizes,
+        counters, status)."""
+        run = self.flat["run"]
+        n = run["histories"] if batchsize is None else batchsize
+        inactive = run["inactive"] if inactive is None else inactive
+        active = run["active"] if active is None else active
+        tracking = run["tracking"] if tracking is None else tracking
+        scores = np.zeros(max(self.total_bins, 1))
+        squares = np.zeros(max(self.total_bins, 1))
+        k = np.zeros(inactive + active)
+        sizes = np.zeros(inactive + active, np.uint64)
+        counters = OrcCounters()
+        status = load().orc_keigenvalue_run(
+            C.byref(self.world), C.byref(self.source), self.estimators, self.n_estimators, n, inactive, active,
+            tracking, scores.ctypes.data_as(_pd), squares.ctypes.data_as(_pd), k.ctypes.data_as(_pd),
+            sizes.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(counters))
+        return scores[:self.total_bins], squares[:self.total_bins], k, sizes, counters.as_dict(), status
 
     def trace(self, first, n, *, seed0=None, tracking=None, cap=1 << 16):
         run = self.flat["run"]
