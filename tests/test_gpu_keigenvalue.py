@@ -75,3 +75,22 @@ def test_fission_bank_overflow_is_reported():
     with pytest.raises(capi.MinimcError) as e:
         drv.solve()
     assert e.value.status == capi.ERR_CAPACITY
+
+
+def test_python_distributed_driver_equals_cpp_host_at_one_rank():
+    """minimc_b200.distributed.KEigenvalue (the multi-GPU orchestration; here world_size 1) and the C++ host's
+    KEigenvalue::Solve run the same device entry points: identical k per cycle and tallies."""
+    import torch
+    from minimc_b200 import distributed
+    text = decks.k_slab(histories=30_000, inactive=2, active=4)
+    flat = util.flat_from_xml(text)
+    drv = capi.Driver(text=text)
+    scores, squares = drv.solve()
+    _, _, k_cycle = drv.keff()
+    world = util.product_world(flat)
+    run = flat["run"]
+    kd = distributed.KEigenvalue(world, util.product_source(flat), util.product_estimators(flat), run["histories"],
+                                 run["inactive"], run["active"], tracking=run["tracking"])
+    out = kd.solve(device=torch.device("cuda", 0))
+    assert np.array_equal(out["k_cycle"], k_cycle)
+    assert np.array_equal(out["scores"], scores) and np.array_equal(out["square_scores"], squares)
