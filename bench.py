@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the history transport loop: particle histories per second.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
-Workload (config.workload): BASELINE.json configs[0] / SURVEY.md M1 = test/multigroup_critical.xml scaled --
-one-group infinite medium, c = 0.25, surface tracking, minstd_compat RNG (bit-exact with the reference), plus a
-`current` estimator on the sphere so the tally path is live.  configs[1..4] (continuous-energy + S(a,b) decks)
-cannot be run by anyone here: every *.hdf5 they need is a git-lfs pointer; north_star's numeric
-target (>= 1e9 multigroup histories/s per B200) is quoted on this multigroup workload.
+Workloads (config.workload) -- BASELINE.json `configs`:
+  single_zone (default)   configs[1] benchmarks/single_zone.xml as shipped: continuous-energy + S(a,b) thermal
+                          scattering, 5 cm slab of H-in-H2O at 450 K, surface tracking, one current estimator with
+                          103 x 101 = 10403 bins.  The deck's *.hdf5 are git-lfs pointers, so the
+                          tables are the synthetic full-shape tables of minimc_b200/ce_decks.py ("data": "synthetic"),
+                          the same files for the GPU and for the reference binary.
+  multigroup_critical     configs[0] test/multigroup_critical.xml: 1-group infinite medium, c = 0.25, plus a
+                          `current` estimator so the tally path is live; north_star's ">= 1e9 multigroup histories/s
+                          per B200" is quoted on this one.  It is also measured (3 steps) inside the default run and
+                          reported under "multigroup" in the same JSON line.
+  continuous_temperature  configs[4]: cell delta tracking, linear T(x), 202 energy bins.
 
-A step = one pass of the hot path over HISTORIES_PER_GPU histories per GPU (weak scaling): rank r transports
+A step = one pass of the hot path over --histories-per-gpu histories per GPU (weak scaling): rank r transports
 histories [r*n, (r+1)*n) of the N*n total, then the integer tallies and counters are all-reduced (NCCL).
 `value`  : device-timed (CUDA events on the launch stream), tables resident in HBM.
-`e2e`    : the same step through the reference-facing C ABI with HOST buffers: flatten -> mmc_world_create (H2D
-           of the tables) -> mmc_fixed_source_run (H2D of bin boundaries, D2H of tallies + counters) -> destroy.
-`--impl reference` times the reference's own C++ (oracle/_ref/ref_harness = /root/reference/src behind shims) on
-the host cores; without a prebuilt oracle/_ref it times the oracle port instead and says so.
+`e2e`    : the same step through the reference-facing call with HOST buffers: Driver::Solve() of the C++ host after
+           dropping its device tables -- flatten -> mmc_world_create (H2D of the tables) -> mmc_fixed_source_run (H2D
+           of the bin boundaries, D2H of tallies + counters).
+`--impl reference` times the reference's own C++ (oracle/_ref/ref_harness = /root/reference/src behind shims) on the
+host cores on a bounded sample of the same deck; without a prebuilt oracle/_ref it says so.
 """
 from __future__ import annotations
 
@@ -30,12 +37,22 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, os.fspath(ROOT))
-sys.path.insert(0, os.fspath(ROOT / "tests"))
 
-HISTORIES_PER_GPU = 1 << 30          # per step
-CPU_SAMPLE_HISTORIES = 20_000_000    # bounded sample of the same workload for the CPU baseline
 METRIC = "particle histories/sec"
-WORKLOAD = "multigroup_critical (BASELINE configs[0], SURVEY M1): 1-group infinite medium c=0.25, surface tracking"
+WORKLOADS = {
+    "single_zone": {
+        "name": "single_zone (BASELINE configs[1], benchmarks/single_zone.xml as shipped): CE + S(a,b) H-in-H2O slab "
+                "5 cm at 450 K, surface tracking, 10403-bin current estimator, synthetic full-shape tables (rank 10, "
+                "partitions up to 97x18x294)",
+        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+    "continuous_temperature": {
+        "name": "continuous_temperature (BASELINE configs[4]): CE + S(a,b) slab, cell delta tracking, linear T(x) "
+                "300..600 K, synthetic full-shape tables",
+        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+    "multigroup_critical": {
+        "name": "multigroup_critical (BASELINE configs[0], SURVEY M1): 1-group infinite medium c=0.25, surface tracking",
+        "histories_per_gpu": 1 << 30, "cpu_rate_guess": 4.0e6},
+}
 
 
 def measured_peak_gbs():
@@ -45,11 +62,11 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def dram_traffic_per_launch():
+def dram_traffic_per_launch(workload):
     """dram__bytes_read+write per launch of the fused kernel from the committed ncu capture, if any."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
-        return json.loads(p.read_text()).get("fixed_source_kernel_dram_bytes_per_launch")
+        return json.loads(p.read_text()).get(workload)
     return None
 
 
@@ -103,27 +120,43 @@ def algorithmic_bytes(c: dict) -> int:
     return 72 * c["n_births"] + 144 * c["n_events"] + 16 * c["n_scores"] + 144 * c["n_banked"]
 
 
-def critical_deck(histories: int, threads: int) -> str:
-    from minimc_b200 import decks
-    return decks.critical(histories=histories, threads=threads, estimators=[{"name": "leakage", "surface": "sphere"}])
+def deck_text(workload: str, table_dir, histories: int, threads: int) -> str:
+    from minimc_b200 import ce_decks, decks
+    if workload == "multigroup_critical":
+        return decks.critical(histories=histories, threads=threads, estimators=[{"name": "leakage", "surface": "sphere"}])
+    if workload == "single_zone":
+        return ce_decks.single_zone_benchmark_deck(table_dir, histories=histories, threads=threads)
+    if workload == "continuous_temperature":
+        return ce_decks.continuous_temperature_deck(table_dir, histories=histories, threads=threads, n_energy_bins=201)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def make_tables(workload: str):
+    """Synthetic full-shape tables in a temp dir (the generator is deterministic, exact arithmetic only)."""
+    if workload == "multigroup_critical":
+        return None
+    from minimc_b200 import ce_decks
+    d = tempfile.mkdtemp(prefix="mmc_tables_")
+    ce_decks.generate_tables(d, "full")
+    return d
 
 
 # --------------------------------------------------------------------- CPU arm
-def time_reference_cpu(histories: int, threads: int):
-    """Wall time of Driver::Solve() of the reference's own code on `threads` host threads."""
-    from oracle import port_py
-    deck = critical_deck(histories, threads)
-    if port_py.ref_available():
-        with tempfile.TemporaryDirectory() as d:
-            path = Path(d) / "critical.xml"
-            path.write_text(deck)
-            _, seconds = port_py.ref_run(path)
-        return seconds, "reference"
-    import util
-    prob = util.oracle_problem(util.flat_from_xml(deck))
-    t0 = time.perf_counter()
-    prob.run(threads=threads)
-    return time.perf_counter() - t0, "port"
+REF_HARNESS = ROOT / "oracle" / "_ref" / "ref_harness"
+
+
+def time_reference_cpu(workload: str, table_dir, histories: int, threads: int):
+    """Wall time of Driver::Solve() of the reference's own code on `threads` host threads (oracle/_ref).  This is the
+    one place bench.py executes anything under oracle/ (the cpu_baseline / reference arm)."""
+    if not (REF_HARNESS.exists() and os.access(REF_HARNESS, os.X_OK)):
+        return None, "reference binary oracle/_ref/ref_harness was not built"
+    with tempfile.TemporaryDirectory() as d:
+        path = Path(d) / "deck.xml"
+        path.write_text(deck_text(workload, table_dir, histories, threads))
+        p = subprocess.run([os.fspath(REF_HARNESS), "run", os.fspath(path)], capture_output=True, text=True)
+        if p.returncode != 0:
+            return None, f"reference failed: {p.stderr.strip()[-200:]}"
+        return float(p.stderr.strip().split("solve_seconds=")[-1]), "reference"
 
 
 def run_reference_arm(args):
@@ -131,21 +164,27 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # a step = a bounded sample of the workload, sized so K + W steps end within a few minutes
-    sample = 5_000_000
+    w = WORKLOADS[args.workload]
+    table_dir = make_tables(args.workload)
+    # a step = a bounded sample of the workload, sized (from a short probe) to ~10 s so K + W steps end within minutes
+    probe = max(int(w["cpu_rate_guess"] * 0.5), 1000)
+    seconds, kind = time_reference_cpu(args.workload, table_dir, probe, cores)
+    if seconds is None:
+        print(json.dumps({"impl": "reference", "unavailable": kind}), flush=True)
+        return
+    sample = max(int(probe / max(seconds, 1e-3) * 10.0), probe)
     for _ in range(args.warmup):
-        time_reference_cpu(sample // 10, cores)
+        time_reference_cpu(args.workload, table_dir, max(sample // 10, 1000), cores)
     total = 0.0
-    kind = "reference"
     for _ in range(args.steps):
-        seconds, kind = time_reference_cpu(sample, cores)
+        seconds, kind = time_reference_cpu(args.workload, table_dir, sample, cores)
         total += seconds
     value = sample * args.steps / total
     line = {
         "metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD, "histories_per_step": sample, "rng": "std::minstd_rand (reference)"},
+        "config": {"workload": w["name"], "histories_per_step": sample, "rng": "std::minstd_rand (reference)"},
         "cpu_baseline": {"value": value, "unit": "histories/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} histories per step, Driver::Solve() wall time, {cores} threads"},
         "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -155,44 +194,30 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------- GPU arm
-def run_gpu_arm(args):
-    import numpy as np
+def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
+    """One workload on this rank's GPU; returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
-    import util
     from minimc_b200 import capi, distributed
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available() or capi.load().mmc_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: minimc_b200 has no CPU transport path")
-    torch.cuda.set_device(local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    n_per_gpu = args.histories_per_gpu
+    rank, local_rank, world_size, dev, stream = ctx
+    w = WORKLOADS[workload]
+    table_dir = make_tables(workload)
     total_histories = n_per_gpu * world_size
-    flat = util.flat_from_xml(critical_deck(min(total_histories, 2 ** 31 - 1), 1))
-    fw = capi.FlatWorld(**flat["world"])
-    world = capi.World(fw, device=local_rank)
-    src, est = util.product_source(flat), util.product_estimators(flat)
+    drv = capi.Driver(text=deck_text(workload, table_dir, total_histories, 1))
+    drv.set_options(device=local_rank)
     first, count = distributed.shard(0, total_histories, rank, world_size)
-
-    scores = torch.zeros(max(est.total_bins, 1), dtype=torch.int64, device=dev)
+    bins = max(drv.total_bins, 1)
+    n_counters = len(capi.Counters._fields_)
+    scores = torch.zeros(bins, dtype=torch.int64, device=dev)
     squares = torch.zeros_like(scores)
-    counters = torch.zeros(len(capi.Counters._fields_), dtype=torch.int64, device=dev)
+    counters = torch.zeros(n_counters, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    # a real (non-default) stream: its handle is what the C ABI launches on and what the CUDA events time
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
 
     def step():
         scores.zero_(), squares.zero_(), counters.zero_()
-        world.fixed_source_run_device(src, est, 1, first, count, scores.data_ptr(), squares.data_ptr(),
-                                      counters.data_ptr(), stream=stream.cuda_stream)
+        drv.run_device(first, count, scores.data_ptr(), squares.data_ptr(), counters.data_ptr(), stream.cuda_stream)
         distributed.allreduce_sum_(scores, squares, counters)
 
     def sync_all():
@@ -200,25 +225,22 @@ def run_gpu_arm(args):
         if world_size > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     sync_all()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kernel_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kernel_ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(steps)] for _ in range(4)]
+    starts, ends, kernel_starts, kernel_ends = ev
     sync_all()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.fill_(k)  # evict L2 between timed iterations (untimed)
         starts[k].record(stream)
         scores.zero_(), squares.zero_(), counters.zero_()
         kernel_starts[k].record(stream)
-        world.fixed_source_run_device(src, est, 1, first, count, scores.data_ptr(), squares.data_ptr(),
-                                      counters.data_ptr(), stream=stream.cuda_stream)
+        drv.run_device(first, count, scores.data_ptr(), squares.data_ptr(), counters.data_ptr(), stream.cuda_stream)
         kernel_ends[k].record(stream)
         distributed.allreduce_sum_(scores, squares, counters)
         ends[k].record(stream)
@@ -232,61 +254,107 @@ def run_gpu_arm(args):
     step_ms, kernel_ms = t.tolist()
     c = dict(zip([n for n, _ in capi.Counters._fields_], counters.tolist()))
     assert c["n_histories"] == total_histories, (c["n_histories"], total_histories)
-    assert c["n_lost"] == 0 and c["n_physics_errors"] == 0 and c["n_capacity_overflow"] == 0
-    value = total_histories * args.steps / (step_ms * 1e-3)
+    assert c["n_lost"] == 0 and c["n_physics_errors"] == 0 and c["n_capacity_overflow"] == 0, c
+    value = total_histories * steps / (step_ms * 1e-3)
 
-    # ---- e2e: the plugin call with HOST buffers (world upload + run + tallies back), every step
-    e2e_steps = max(1, min(args.steps, 3))
-    wd_bytes = sum(getattr(fw, name).nbytes for name in capi.FlatWorld.FIELDS)
-    h2d = wd_bytes + 8 * 0  # tables (this deck has no bin-boundary arrays)
-    d2h = 2 * 8 * max(est.total_bins, 1) + 8 * len(capi.Counters._fields_)
+    # ---- e2e: Driver::Solve() with HOST buffers, tables uploaded again every step
+    e2e_steps = max(1, min(steps, 3))
+    drv.set_shard(rank, world_size)
+    h2d = drv.table_bytes + 8 * bins  # tables + (upper bound of) the bin-boundary array
+    d2h = 2 * 8 * bins + 8 * n_counters
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        w2 = capi.World(fw, device=local_rank)
-        h_scores, h_squares, h_counters = w2.fixed_source_run(src, est, 1, first, count)
-        w2.close()
+        drv.release_device()
+        drv.solve()
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_histories * e2e_steps / t.item()
+    drv.close()
+    if rank != 0:
+        return None
 
+    peak, peak_src = measured_peak_gbs()
+    per_rank = {k: v / world_size for k, v in c.items()}
+    bytes_per_launch = algorithmic_bytes(per_rank)
+    launch_s = kernel_ms * 1e-3 / steps
+    achieved = bytes_per_launch / launch_s / 1e9
+    result = {
+        "value": value, "ms_per_step": step_ms / steps, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": dram_traffic_per_launch(workload), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": 1e3 * launch_s,
+                     "note": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4); the fused "
+                             "kernel keeps particle state in registers and the tables in L2/SMEM, so real DRAM traffic "
+                             "is far below this model: the kernel is fp64-issue bound, see DESIGN.md"},
+        "counters_per_step": c,
+        "config": {"workload": w["name"], "histories_per_gpu_per_step": n_per_gpu, "rng": "minstd_compat (bit-exact)",
+                   "estimator_bins": int(bins), "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "parallelism": f"histories sharded over {world_size} GPU(s), final all-reduce of integer tallies"},
+    }
+    if cpu_baseline:
+        cores = os.cpu_count() or 1
+        probe = max(int(w["cpu_rate_guess"] * 0.5), 1000)
+        seconds, kind = time_reference_cpu(workload, table_dir, probe, cores)
+        if seconds is not None:
+            sample = max(int(probe / max(seconds, 1e-3) * 15.0), probe)  # ~15 s of CPU work
+            seconds, kind = time_reference_cpu(workload, table_dir, sample, cores)
+            result["cpu_baseline"] = {
+                "value": sample / seconds, "unit": "histories/s", "cores": cores, "kind": kind,
+                "sample": f"{sample} histories of the same deck and tables, Driver::Solve() wall time, {cores} threads"}
+        else:
+            result["cpu_baseline"] = {"value": None, "unit": "histories/s", "cores": cores, "kind": "reference",
+                                      "sample": kind}
+    return result
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from minimc_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available() or capi.load().mmc_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: minimc_b200 has no CPU transport path")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    # a real (non-default) stream: its handle is what the C ABI launches on and what the CUDA events time
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = (rank, local_rank, world_size, dev, stream)
+
+    n_per_gpu = args.histories_per_gpu or WORKLOADS[args.workload]["histories_per_gpu"]
+    main = measure(args, args.workload, n_per_gpu, args.steps, args.warmup, ctx,
+                   cpu_baseline=world_size == 1 and not args.no_cpu_baseline)
+    extra = None
+    if args.workload != "multigroup_critical" and not args.no_multigroup:
+        extra = measure(args, "multigroup_critical", WORKLOADS["multigroup_critical"]["histories_per_gpu"], 3, 3, ctx,
+                        cpu_baseline=False)
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        per_rank = {k: v / world_size for k, v in c.items()}
-        bytes_per_launch = algorithmic_bytes(per_rank)
-        launch_s = kernel_ms * 1e-3 / args.steps
-        achieved = bytes_per_launch / launch_s / 1e9
-        cpu_value, cpu = None, None
-        if world_size == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            seconds, kind = time_reference_cpu(CPU_SAMPLE_HISTORIES, cores)
-            cpu_value = CPU_SAMPLE_HISTORIES / seconds
-            cpu = {"value": cpu_value, "unit": "histories/s", "cores": cores, "kind": kind,
-                   "sample": f"{CPU_SAMPLE_HISTORIES} histories of the same deck, Driver::Solve() wall time, "
-                             f"{cores} threads"}
         line = {
-            "metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": world_size, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "histories_per_gpu_per_step": n_per_gpu, "rng": "minstd_compat (bit-exact)",
-                       "tracking": "surface", "estimators": 1, "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "parallelism": f"histories sharded over {world_size} GPU(s), final all-reduce of integer tallies"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
-            "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": dram_traffic_per_launch(), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": 1e3 * launch_s,
-                         "note": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4); the fused "
-                                 "kernel keeps particle state in registers, so real DRAM traffic is far below this"},
-            "counters_per_step": c,
+            "metric": METRIC, "value": main["value"], "unit": "histories/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main["config"], "clocks": main["clocks"],
+            "e2e": main["e2e"], "gpu_launches": args.steps, "roofline": main["roofline"],
+            "counters_per_step": main["counters_per_step"],
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if "cpu_baseline" in main:
+            line["cpu_baseline"] = main["cpu_baseline"]
+        if extra is not None:
+            line["multigroup"] = {"workload": extra["config"]["workload"], "value": extra["value"], "unit": "histories/s",
+                                  "steps": 3, "ms_per_step": extra["ms_per_step"], "e2e": extra["e2e"],
+                                  "roofline_frac": extra["roofline"]["frac"],
+                                  "histories_per_gpu_per_step": extra["config"]["histories_per_gpu_per_step"]}
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()
@@ -298,8 +366,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--histories-per-gpu", type=int, default=HISTORIES_PER_GPU)
+    ap.add_argument("--workload", default="single_zone", choices=sorted(WORKLOADS))
+    ap.add_argument("--histories-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multigroup", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -253,6 +253,9 @@ int mmc_device_count(void);
 int mmc_world_create(const mmc_world_desc* desc, int device, mmc_world** out);
 void mmc_world_destroy(mmc_world* world);
 
+/* Bytes of flattened tables resident on the device for this world (what mmc_world_create copied host -> device). */
+uint64_t mmc_world_bytes(const mmc_world* world);
+
 /* Total number of bins of estimator e = cosine.n_bins * energy.n_bins
  * (ParticleBins::size, Bins.cpp:192-194). */
 uint64_t mmc_estimator_size(const mmc_estimator_desc* e);
@@ -379,6 +382,14 @@ int mmc_driver_counters(const mmc_driver* driver, mmc_counters* counters);
 size_t mmc_driver_output(const mmc_driver* driver, char* buf, size_t cap);
 /* The flattened World as JSON with C99 hex floats (test hook). */
 size_t mmc_driver_world_json(const mmc_driver* driver, char* buf, size_t cap);
+/* Device-resident form of Solve() for fixed-source decks (mmc_fixed_source_run_device with the driver's world,
+ * source and estimators): histories [first_history, first_history + n_histories) of seed `Driver::seed`, integer
+ * tallies accumulated into DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the library's stream). */
+int mmc_driver_run_device(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, uint64_t* d_scores,
+                          uint64_t* d_square_scores, mmc_counters* d_counters, void* stream);
+/* Drops the device copy of the World, so that the next Solve() uploads the tables again; and its size in bytes. */
+void mmc_driver_release_device(mmc_driver* driver);
+uint64_t mmc_driver_table_bytes(mmc_driver* driver);
 /* Parity hook: mmc_trace_histories for histories [first, first + n) of a fixed-source deck. */
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records);

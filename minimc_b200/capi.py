@@ -105,7 +105,7 @@ EXPORTS = (
     "mmc_driver_create", "mmc_driver_create_from_string", "mmc_driver_destroy", "mmc_driver_set_options",
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
-    "mmc_driver_trace",
+    "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
 )
 
 _lib = None
@@ -201,6 +201,14 @@ def load() -> C.CDLL:
     lib.mmc_driver_trace.restype = C.c_int
     lib.mmc_driver_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(EventRecord), C.c_size_t,
                                      C.POINTER(C.c_size_t)]
+    lib.mmc_driver_run_device.restype = C.c_int
+    lib.mmc_driver_run_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mmc_driver_release_device.restype = None
+    lib.mmc_driver_release_device.argtypes = [C.c_void_p]
+    lib.mmc_driver_table_bytes.restype = C.c_uint64
+    lib.mmc_driver_table_bytes.argtypes = [C.c_void_p]
+    lib.mmc_world_bytes.restype = C.c_uint64
+    lib.mmc_world_bytes.argtypes = [C.c_void_p]
     lib.mmc_driver_keff.restype = C.c_int
     lib.mmc_driver_keff.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t)]
     if lib.mmc_abi_version() != ABI_VERSION:
@@ -504,6 +512,17 @@ class Driver:
         if not text:
             raise MinimcError(ERR_INVALID, last_error())
         return json.loads(text)
+
+    def run_device(self, first_history, n_histories, d_scores, d_square, d_counters, stream=None):
+        """mmc_driver_run_device: raw device pointers (ints), asynchronous on `stream` (a cudaStream_t handle)."""
+        check(load().mmc_driver_run_device(self._handle, first_history, n_histories, d_scores, d_square, d_counters, stream))
+
+    def release_device(self):
+        load().mmc_driver_release_device(self._handle)
+
+    @property
+    def table_bytes(self) -> int:
+        return int(load().mmc_driver_table_bytes(self._handle))
 
     def trace(self, first_history: int, n_histories: int, cap=1 << 18):
         records = (EventRecord * cap)()

@@ -344,6 +344,27 @@ def slab_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking=None,
     return s
 
 
+def single_zone_benchmark_deck(table_dir, *, histories=1000000, threads=8, seed=None) -> str:
+    """benchmarks/single_zone.xml as shipped (BASELINE configs[1]) with the table paths rewritten: 5 cm slab, global
+    constant temperature 450 K, data evaluated at 293.6 K, surface tracking, one `current` estimator on the right
+    plane with 101 linspace cosine bins x 99 linspace energy bins (103 x 101 = 10 403 bins with the end bins)."""
+    s = "<minimc>\n" + _general(histories, threads, seed, "surface").replace("<chunksize>100000", "<chunksize>10000")
+    s += "<nuclides>\n  <continuous>\n" + _hydrogen(table_dir, "293K", 293.6) + "  </continuous>\n</nuclides>\n"
+    s += '<materials>\n  <material name="hydrogen in water" aden="0.066854">\n    <nuclide name="hydrogen in water" afrac="1"/>\n  </material>\n</materials>\n'
+    s += '<surfaces>\n  <planex name="left-plane" x="-1e-6"/>\n  <planex name="right-plane" x="5.0"/>\n</surfaces>\n'
+    s += ('<cells>\n  <void>\n    <surface name="left-plane" sense="-1"/>\n  </void>\n'
+          '  <cell name="segment" material="hydrogen in water">\n'
+          '    <surface name="left-plane" sense="+1"/>\n    <surface name="right-plane" sense="-1"/>\n  </cell>\n'
+          '  <void>\n    <surface name="right-plane" sense="+1"/>\n  </void>\n</cells>\n')
+    s += _source(0.56e-6)
+    s += '<temperature>\n  <constant c="450.0"/>\n</temperature>\n'
+    s += ('<estimators>\n  <current name="leakage" surface="right-plane">\n    <bins>\n'
+          '      <cosine u="1.0" v="0.0" w="0.0">\n        <linspace min="0" max="1.01" bins="101" />\n      </cosine>\n'
+          '      <energy>\n        <linspace min="1e-11" max="0.8e-6" bins="99" />\n      </energy>\n'
+          '    </bins>\n  </current>\n</estimators>\n</minimc>\n')
+    return s
+
+
 def multi_zone_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking="surface", n_energy_bins=40) -> str:
     """benchmarks/multi_zone.xml: 13 slab segments at 300..600 K between 14 planes, tabulated data at 623.6 K."""
     planes = [-1e-6, 0.33, 0.67, 1.00, 1.33, 1.67, 2.00, 2.33, 2.67, 3.00, 3.33, 3.67, 4.00, 4.33]

@@ -395,6 +395,8 @@ int mmc_device_count(void) {
   return n;
 }
 
+uint64_t mmc_world_bytes(const mmc_world* world) { return world ? world->blob_bytes : 0; }
+
 uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
   if (!e) return 0;
   auto n = [](const mmc_bins_desc& b) -> uint64_t { return b.kind == MMC_BINS_NONE ? 1 : b.n_bins; };

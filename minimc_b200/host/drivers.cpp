@@ -135,6 +135,18 @@ EstimatorSet FixedSource::Solve() {
   return result;
 }
 
+void FixedSource::RunDevice(
+    uint64_t first, uint64_t count, uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters, void* stream) {
+  if (device_estimators_.empty() && !init_estimator_set.estimators.empty()) device_estimators_ = FlattenEstimators(init_estimator_set);
+  mmc_run_options options = run_options;
+  options.tracking = tracking;
+  options.stream = stream;
+  const int status = mmc_fixed_source_run_device(
+      device_world()->handle, &source.desc, device_estimators_.data(), static_cast<int32_t>(device_estimators_.size()), seed,
+      first, count, &options, d_scores, d_square_scores, d_counters);
+  if (status != MMC_OK) ThrowLastError("mmc_fixed_source_run_device", status);
+}
+
 std::vector<mmc_event_record> FixedSource::Trace(uint64_t first, uint64_t count, size_t cap) {
   std::vector<mmc_event_record> records(cap);
   size_t n = 0;

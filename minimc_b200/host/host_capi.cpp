@@ -146,6 +146,31 @@ size_t mmc_driver_world_json(const mmc_driver* driver, char* buf, size_t cap) {
   }
 }
 
+int mmc_driver_run_device(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, uint64_t* d_scores,
+                          uint64_t* d_square_scores, mmc_counters* d_counters, void* stream) {
+  return Guard([&] {
+    if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
+    auto* fixed = dynamic_cast<minimc::FixedSource*>(driver->driver.get());
+    if (!fixed) return mmc::set_last_error(MMC_ERR_INVALID, "not a fixed-source problem");
+    fixed->RunDevice(first_history, n_histories, d_scores, d_square_scores, d_counters, stream);
+    return static_cast<int>(MMC_OK);
+  });
+}
+
+void mmc_driver_release_device(mmc_driver* driver) {
+  if (driver) driver->driver->ReleaseDevice();
+}
+
+uint64_t mmc_driver_table_bytes(mmc_driver* driver) {
+  if (!driver) return 0;
+  try {
+    return driver->driver->DeviceTableBytes();
+  } catch (const std::exception& e) {
+    mmc::set_last_error(MMC_ERR_INVALID, e.what());
+    return 0;
+  }
+}
+
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records) {
   return Guard([&] {

@@ -276,10 +276,14 @@ public:
   // [r*N/P, (r+1)*N/P); the caller reduces EstimatorSets with operator+=
   int rank = 0, world_size = 1;
   mmc_counters counters{};
+  // Drops the device copy of the World (the next Solve() uploads it again); bytes it holds.
+  void ReleaseDevice() { device_world_.reset(); }
+  uint64_t DeviceTableBytes() { return mmc_world_bytes(device_world_handle()); }
+
+  const mmc_world* device_world_handle();
 
 protected:
   std::shared_ptr<DeviceWorld> device_world();
-  const mmc_world* device_world_handle();
 
 private:
   std::shared_ptr<DeviceWorld> device_world_;
@@ -290,11 +294,16 @@ class FixedSource : public Driver {
 public:
   explicit FixedSource(const xml::Node& root);
   EstimatorSet Solve() override;
+  // Device-resident Solve(): integer tallies of histories [first, first + count) accumulated into device buffers,
+  // asynchronous on `stream`.
+  void RunDevice(uint64_t first, uint64_t count, uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters,
+                 void* stream);
   // Parity hook (mmc_trace_histories): per-event records of histories [first, first + count).
   std::vector<mmc_event_record> Trace(uint64_t first, uint64_t count, size_t cap = size_t{1} << 20);
 
 private:
   const Source source;
+  std::vector<mmc_estimator_desc> device_estimators_;  // points into init_estimator_set
 };
 
 // KEigenvalue (KEigenvalue.cpp:17-86 is a stub in the reference, SURVEY.md F1;
