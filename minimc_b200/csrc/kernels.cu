@@ -26,6 +26,14 @@
 #include "kernels.h"
 #include "transport.cuh"
 
+// resident CTAs per SM the register allocation is tuned for (measured choices)
+#ifndef MMC_CE_BLOCKS_PER_SM
+#define MMC_CE_BLOCKS_PER_SM 3
+#endif
+#ifndef MMC_MG_BLOCKS_PER_SM
+#define MMC_MG_BLOCKS_PER_SM 3
+#endif
+
 namespace mmc {
 
 namespace {
@@ -90,7 +98,7 @@ __device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t
 // (count, start) per parent let order_bank_kernel restore the deterministic
 // (parent index, creation ordinal) order.
 template <int kTracking, bool kCE, bool kGeneration>
-__global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
+__global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM : MMC_MG_BLOCKS_PER_SM) fixed_source_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
     unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters,
@@ -113,6 +121,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
   bool done = false;         // no more work for this lane
   uint64_t w_next = 0, w_end = 0;  // warp-uniform chunk of history indices
   uint64_t history = 0;            // index of this lane's current history
+  // isotropic direction owed to this lane: bit 0 = its multigroup scatter of the previous iteration, bit 1 = it
+  // was just born from an isotropic source.  Both are the same code on the lane's rng, so they run converged.
+  uint32_t owed = 0;
   ThreadCounters c;
 
   while (true) {
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
           n_pending = 0;
           history = idx;
           if (kGeneration) load_site(bank.in[idx], p);
-          else sample_source(run.source, run.seed0 + run.first_history + idx, p);
+          else if (sample_source(run.source, run.seed0 + run.first_history + idx, p, true)) owed |= 2u;
           alive = true;
           c.histories++;
           c.births++;
@@ -172,9 +183,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
     }
     if (__all_sync(kFull, done)) break;
 
+    // ---- isotropic directions owed to scattered and newly born lanes (Point.cpp:89-96)
+    if (owed) {
+      isotropic_direction(p.rng, p.dx, p.dy, p.dz);
+      if (owed & 2u) finish_source(p);
+      owed = 0;
+    }
+
     // ---- one event per live lane
     StepOut o;
     o.secondaries = 0;
+    o.need_direction = false;
     o.error_physics = o.error_capacity = o.error_lost = false;
     if (alive) {
       if (p.cell < 0) {
@@ -185,7 +204,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock) fixed_source_kernel(
           p.event = MMC_EV_LEAK;
         }
       }
-      if (p.cell >= 0) transport_step<kTracking, kCE>(w, p, dq, o);
+      if (p.cell >= 0) transport_step<kTracking, kCE, true>(w, p, dq, o);
+      if (o.need_direction) owed |= 1u;
       count_event(c, p, o);
     }
     if (kGeneration) {

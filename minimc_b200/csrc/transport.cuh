@@ -104,7 +104,7 @@ __device__ __forceinline__ void normalize(double& x, double& y, double& z) {
 }
 
 // Direction(const Direction& d, mu, phi): Point.cpp:98-121
-__device__ inline void rotate_direction(
+__device__ __noinline__ void rotate_direction(
     double dx, double dy, double dz, double mu, double phi, double& ox, double& oy, double& oz) {
   const bool off_xaxis = dx <= 0.9 && dx > -0.9;
   const double ax = off_xaxis ? 1.0 : 0.0, ay = off_xaxis ? 0.0 : 1.0, az = 0.0;
@@ -243,12 +243,24 @@ __device__ __forceinline__ void stream(Particle& p, double d) {
 
 // ------------------------------------------------------------------- source
 // Source::Sample, Source.cpp:143-154
-__device__ inline void sample_source(const SourceSpec& src, uint64_t seed, Particle& p) {
+// With defer_isotropic the isotropic direction is NOT drawn here: the particle's rng is left holding the SOURCE
+// stream (std::minstd_rand{seed}) and the function returns true; the caller then runs
+// isotropic_direction(p.rng, ...) followed by finish_source(p), which together are the rest of Source::Sample.
+__device__ inline bool sample_source(const SourceSpec& src, uint64_t seed, Particle& p, bool defer_isotropic = false) {
   Rng rng{lcg_seed(seed)};
   p.px = src.position[0];
   p.py = src.position[1];
   p.pz = src.position[2];
+  p.group = src.group;
+  p.energy = src.energy;
+  p.cell = -1;
+  p.surface = -1;
+  p.event = MMC_EV_BIRTH;
   if (src.direction_kind == MMC_DIR_ISOTROPIC) {
+    if (defer_isotropic) {
+      p.rng = rng;
+      return true;
+    }
     isotropic_direction(rng, p.dx, p.dy, p.dz);
   } else if (src.direction_kind == MMC_DIR_ISOTROPIC_FLUX) {
     // IsotropicFlux::Sample, Source.cpp:124-129
@@ -260,13 +272,12 @@ __device__ inline void sample_source(const SourceSpec& src, uint64_t seed, Parti
     p.dy = src.direction[1];
     p.dz = src.direction[2];
   }
-  p.group = src.group;
-  p.energy = src.energy;
   p.rng.x = lcg_seed(rng.raw());  // Particle ctor: rng{seed}
-  p.cell = -1;
-  p.surface = -1;
-  p.event = MMC_EV_BIRTH;
+  return false;
 }
+
+// auto sampled_seed = rng(); Particle{..., sampled_seed} (Source.cpp:149-153)
+__device__ __forceinline__ void finish_source(Particle& p) { p.rng.x = lcg_seed(p.rng.raw()); }
 
 // ------------------------------------------------------- secondary particles
 // Per-thread ring deque in global scratch reproducing the bank order of
@@ -283,6 +294,7 @@ struct SiteDeque {
 // ----------------------------------------------------------- multigroup step
 struct StepOut {
   uint32_t secondaries;  // produced by this event
+  bool need_direction;   // a multigroup scatter left its isotropic direction to the caller (kDeferDirection)
   bool error_physics;
   bool error_capacity;
   bool error_lost;
@@ -305,6 +317,7 @@ __device__ __forceinline__ double material_micro_total(const WorldView& w, int32
 
 // Multigroup::Interact and its Capture/Scatter/Fission (Multigroup.cpp:49-73,
 // 245-287) after Particle::SampleNuclide (Particle.cpp:110-124).
+template <bool kDeferDirection>
 __device__ inline void collide_multigroup(
     const WorldView& w, Particle& p, int32_t mat, double micro_total, SiteDeque& dq, StepOut& out) {
   const int32_t G = w.h->n_groups;
@@ -365,7 +378,10 @@ __device__ inline void collide_multigroup(
       return;
     }
     p.group = static_cast<uint64_t>(g + 1);
-    isotropic_direction(p.rng, p.dx, p.dy, p.dz);
+    // SetDirectionIsotropic (Multigroup.cpp:258-259): the next draws of p.rng; the fused kernel runs it together
+    // with the source directions of newly born lanes so that the warp stays converged on the sincos
+    if (kDeferDirection) out.need_direction = true;
+    else isotropic_direction(p.rng, p.dx, p.dy, p.dz);
   } else if (reaction == 2) {
     // Multigroup::Fission, Multigroup.cpp:267-287
     p.event = MMC_EV_FISSION;
@@ -424,9 +440,10 @@ namespace mmc {
 // One iteration of SurfaceTracking::Transport (TransportMethod.cpp:56-75) or
 // CellDeltaTracking::Transport (TransportMethod.cpp:92-120).  kCE selects the
 // Continuous (true) or Multigroup (false) Interaction of the world's nuclides.
-template <int kTracking, bool kCE>
+template <int kTracking, bool kCE, bool kDeferDirection = false>
 __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out) {
   out.secondaries = 0;
+  out.need_direction = false;
   out.error_physics = out.error_capacity = out.error_lost = false;
   const int32_t mat = w.at<int32_t>(w.h->off_cell_material)[p.cell];
   if (mat < 0) {  // born in a void cell: the reference dereferences a null Material
@@ -436,6 +453,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
   }
   // GetCollisionProbabilityDensity: total (surface tracking) or majorant (cell delta tracking)
   double micro, majorant;
+  ce::NuclideEval ev;
   if (kCE) {
     bool error = false;
     const double T = ce::cell_temperature(w, p.cell, p.px, p.py, p.pz);
@@ -443,7 +461,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
       majorant = ce::material_majorant(w, mat, p.energy, T, ce::cell_temperature_upper(w, p.cell), error);
       micro = 0;  // evaluated below, only when a collision is a candidate
     } else {
-      micro = majorant = ce::material_total(w, mat, p.energy, T, error);
+      micro = majorant = ce::material_total(w, mat, p.energy, T, error, &ev);
     }
     if (error) {
       out.error_physics = true;
@@ -477,7 +495,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
       // bernoulli_distribution{total / majorant}: u < p, both evaluated BEFORE the particle streams
       if (kCE) {
         bool error = false;
-        micro = ce::material_total(w, mat, p.energy, ce::cell_temperature(w, p.cell, p.px, p.py, p.pz), error);
+        micro = ce::material_total(w, mat, p.energy, ce::cell_temperature(w, p.cell, p.px, p.py, p.pz), error, &ev);
         if (error) {
           out.error_physics = true;
           p.event = MMC_EV_CAPTURE;
@@ -488,8 +506,8 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
     }
     stream(p, d_coll);
     if (real) {
-      if (kCE) ce::collide_continuous(w, p, mat, dq, out);
-      else collide_multigroup(w, p, mat, micro, dq, out);
+      if (kCE) ce::collide_continuous(w, p, mat, dq, out, ev);
+      else collide_multigroup<kDeferDirection>(w, p, mat, micro, dq, out);
     } else {
       p.event = MMC_EV_VIRTUAL_COLLISION;
     }
@@ -498,7 +516,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
 
 // ------------------------------------------------------------------- tallies
 // Bins::GetIndex for each concrete type, Bins.cpp:72-82,112-123,158-162
-__device__ __forceinline__ uint64_t bins_index(const BinsSpec& b, const double* bounds, double v) {
+__device__ __noinline__ uint64_t bins_index(const BinsSpec& b, const double* bounds, double v) {
   switch (b.kind) {
   case MMC_BINS_LINSPACE:
     if (v < b.lower) return 0;
