@@ -340,7 +340,8 @@ int mmc_trace_histories(
 /* Diagnostic (no reference counterpart): evaluates on the device the libm
  * functions the transport kernels use -- the bit-exact restatements of glibc's
  * log (fn 0: out0), sincos (fn 1: out0 = sin, out1 = cos), sin (fn 2), cos
- * (fn 3) -- and the libstdc++ generate_canonical stream (fn 4: x[i] is a seed,
+ * (fn 3), the converged pair used for Direction(d, mu, phi) (fn 5: out0 = sin(x), out1 = cos(x) as two separate
+ * libm calls return them) -- and the libstdc++ generate_canonical stream (fn 4: x[i] is a seed,
  * out0[i] the first canonical double of std::minstd_rand{seed}).  HOST buffers. */
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n);
 

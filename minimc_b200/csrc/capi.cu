@@ -839,7 +839,7 @@ int mmc_test_geometry(const mmc_world* world, size_t n, const double* positions,
 }
 
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n) {
-  if (fn < 0 || fn > 4 || !x || !out0 || (fn == 1 && !out1)) return fail(MMC_ERR_INVALID, "bad arguments");
+  if (fn < 0 || fn > 5 || !x || !out0 || ((fn == 1 || fn == 5) && !out1)) return fail(MMC_ERR_INVALID, "bad arguments");
   if (mmc_device_count() < 1) return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible");
   if (n == 0) return MMC_OK;
   double *d_x = nullptr, *d_0 = nullptr, *d_1 = nullptr;
@@ -849,7 +849,7 @@ int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, si
   if (e == cudaSuccess) e = cudaMemcpy(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = launch_test_math(fn, d_x, d_0, d_1, n, nullptr);
   if (e == cudaSuccess) e = cudaMemcpy(out0, d_0, n * sizeof(double), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && fn == 1) e = cudaMemcpy(out1, d_1, n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && (fn == 1 || fn == 5)) e = cudaMemcpy(out1, d_1, n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d_x);
   cudaFree(d_0);
   cudaFree(d_1);

@@ -245,43 +245,105 @@ MMC_MATH_FN double do_sincos(double a, double da, int n) {
 }
 }  // namespace detail
 
-// s_sincos.c: __sincos
+MMC_MATH_FN double sin(double x);
+MMC_MATH_FN double cos(double x);
+
+// s_sincos.c: __sincos.  glibc picks one of three range reductions and then evaluates, in every one of them,
+// exactly one do_sin and one do_cos on the same reduced argument (a, da) -- only which of the two becomes the sine
+// and the signs differ.  Written that way here (reduce; evaluate both; select) so that the lanes of a warp, whose
+// arguments fall into different ranges and quadrants, execute ONE pass over the expensive table + polynomial code
+// instead of one pass per branch.  The values are glibc's bit for bit (tests/test_glibc_math.py).
 MMC_MATH_FN void sincos(double x, double* sinx, double* cosx) {
   using namespace detail;
   const uint32_t k = static_cast<uint32_t>(as_u64(x) >> 32) & 0x7fffffffu;
-  if (k < 0x400368fdu) {
-    if (k < 0x3e400000u) {  // |x| < 2^-27
-      *sinx = x;
-      *cosx = 1.0;
-      return;
-    }
-    if (k < 0x3feb6000u) {  // |x| < 0.855469: __sin_local, __cos_local
-      const double ax = fabs_(x);
-      double r;
-      const TableEntry e = lookup(ax, r);
-      *sinx = ax < kTaylorLimit ? taylor_sin(x, 0.0) : do_sin_core(x, r, x > 0 ? 0.0 : -0.0, e);
-      *cosx = do_cos_core(r, x >= 0 ? 0.0 : -0.0, e);
-      return;
-    }
-    // |x| < 2.426265
+  if (k >= 0x419921FBu) {  // |x| >= 105414350, inf, nan
+    ::sincos(x, sinx, cosx);
+    return;
+  }
+  if (k < 0x3e400000u) {  // |x| < 2^-27
+    *sinx = x;
+    *cosx = 1.0;
+    return;
+  }
+  double a, da;
+  int n = 0, range;
+  if (k < 0x3feb6000u) {  // |x| < 0.855469: __sin_local, __cos_local on (x, 0)
+    a = x;
+    da = 0.0;
+    range = 0;
+  } else if (k < 0x400368fdu) {  // |x| < 2.426265: pi/2 - |x| in two pieces
     const double y = sub(kHp0, fabs_(x));
-    const double a = add(y, kHp1);
-    const double da = add(sub(y, a), kHp1);
-    const double aa = fabs_(a);
-    double r;
-    const TableEntry e = lookup(aa, r);
-    *sinx = copysign_(do_cos_core(r, a < 0 ? -da : da, e), x);
-    *cosx = aa < kTaylorLimit ? taylor_sin(a, da) : do_sin_core(a, r, a <= 0 ? -da : da, e);
+    a = add(y, kHp1);
+    da = add(sub(y, a), kHp1);
+    range = 1;
+  } else {  // |x| < 105414350: reduce_sincos
+    n = reduce(x, a, da);
+    range = 2;
+  }
+  const double aa = fabs_(a);
+  double r;
+  const TableEntry e = lookup(aa, r);
+  const double sin_like = aa < kTaylorLimit ? taylor_sin(a, da) : do_sin_core(a, r, a <= 0 ? -da : da, e);  // do_sin(a, da)
+  const double cos_like = do_cos_core(r, a < 0 ? -da : da, e);                                               // do_cos(a, da)
+  if (range == 0) {
+    *sinx = sin_like;
+    *cosx = cos_like;
+  } else if (range == 1) {
+    *sinx = copysign_(cos_like, x);
+    *cosx = sin_like;
+  } else {
+    const double sn = (n & 1) ? cos_like : sin_like;        // do_sincos(a, da, n)
+    const double cn = ((n + 1) & 1) ? cos_like : sin_like;  // do_sincos(a, da, n + 1)
+    *sinx = (n & 2) ? -sn : sn;
+    *cosx = ((n + 1) & 2) ? -cn : cn;
+  }
+}
+
+// __sin(x) and __cos(x) as two separate calls return (the reference's Direction(d, mu, phi) calls std::cos and
+// std::sin separately, Point.cpp:117-118), computed in one converged pass like sincos above.  NOT the same values as
+// sincos: in the middle range __sin evaluates do_cos on (pi/2 - |x|, hp1) while __cos and __sincos use the
+// renormalised pair (a, da).
+MMC_MATH_FN void sin_and_cos(double x, double* sinx, double* cosx) {
+  using namespace detail;
+  const uint32_t k = static_cast<uint32_t>(as_u64(x) >> 32) & 0x7fffffffu;
+  if (k >= 0x419921FBu || k < 0x3e500000u) {  // huge / non-finite, or |x| < 2^-26: the scalar functions' own paths
+    *sinx = sin(x);
+    *cosx = cos(x);
     return;
   }
-  if (k < 0x419921FBu) {  // |x| < 105414350
-    double a, da;
-    const int n = reduce(x, a, da);
-    *sinx = do_sincos(a, da, n);
-    *cosx = do_sincos(a, da, n + 1);
-    return;
+  double as, das, ac, dac;  // arguments of the one do_sin and the one do_cos
+  int n = 0, range;
+  if (k < 0x3feb6000u) {  // |x| < 0.855469: sin = do_sin(x, 0), cos = do_cos(x, 0)
+    as = ac = x;
+    das = dac = 0.0;
+    range = 0;
+  } else if (k < 0x400368fdu) {  // |x| < 2.426265: sin = copysign(do_cos(y, hp1), x), cos = do_sin(a, da)
+    const double y = sub(kHp0, fabs_(x));
+    ac = y;
+    dac = kHp1;
+    as = add(y, kHp1);
+    das = add(sub(y, as), kHp1);
+    range = 1;
+  } else {  // reduce_sincos
+    n = reduce(x, as, das);
+    ac = as;
+    dac = das;
+    range = 2;
   }
-  ::sincos(x, sinx, cosx);
+  const double sin_like = do_sin(as, das);
+  const double cos_like = do_cos(ac, dac);
+  if (range == 0) {
+    *sinx = sin_like;
+    *cosx = cos_like;
+  } else if (range == 1) {
+    *sinx = copysign_(cos_like, x);
+    *cosx = sin_like;
+  } else {
+    const double sn = (n & 1) ? cos_like : sin_like;
+    const double cn = ((n + 1) & 1) ? cos_like : sin_like;
+    *sinx = (n & 2) ? -sn : sn;
+    *cosx = ((n + 1) & 2) ? -cn : cn;
+  }
 }
 
 // s_sin.c: __sin

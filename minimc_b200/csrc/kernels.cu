@@ -365,6 +365,8 @@ __global__ void test_math_kernel(int fn, const double* x, double* out0, double* 
     out0[i] = glibc::sin(x[i]);
   } else if (fn == 3) {
     out0[i] = glibc::cos(x[i]);
+  } else if (fn == 5) {
+    glibc::sin_and_cos(x[i], &out0[i], &out1[i]);
   } else {
     Rng rng{lcg_seed(static_cast<uint64_t>(x[i]))};
     out0[i] = rng.canonical();

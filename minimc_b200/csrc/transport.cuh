@@ -119,7 +119,8 @@ __device__ __noinline__ void rotate_direction(
   double vz = __dsub_rn(__dmul_rn(dx, uy), __dmul_rn(dy, ux));
   normalize(vx, vy, vz);
   // separate cos and sin calls in the reference's object code (Point.cpp:117-118)
-  const double c = glibc::cos(phi), s = glibc::sin(phi);
+  double s, c;
+  glibc::sin_and_cos(phi, &s, &c);
   const double sq = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(mu, mu)));
   const double uc = __dmul_rn(sq, c), vc = __dmul_rn(sq, s);
   // (u_comp + v_comp) + d_comp, then Direction(Point&&) normalises

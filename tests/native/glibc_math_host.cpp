@@ -34,7 +34,7 @@ void mmc_host_cos(const double* x, double* y, size_t n) {
 // Sweeps n arguments from a splitmix64 stream over [lo, hi) (uniform in value
 // when mode 0, uniform in bit pattern between lo and hi when mode 1) and
 // returns the number of arguments where the restatement and libm differ.
-// what: 0 log, 1 sincos, 2 sin, 3 cos
+// what: 0 log, 1 sincos, 2 sin, 3 cos, 4 sin_and_cos (vs separate sin, cos)
 uint64_t mmc_host_fuzz(int what, double lo, double hi, int mode, uint64_t n, uint64_t seed, double* first_bad) {
   uint64_t bad = 0, s = seed;
   const uint64_t blo = bits(lo), bhi = bits(hi);
@@ -90,6 +90,9 @@ int main(int argc, char** argv) {
       {"sin bits [2^-30,0.9)", 2, 0x1p-30, 0.9, 1},      {"sin [0,1e5)", 2, 0.0, 1e5, 0},
       {"cos [0,2pi)", 3, 0.0, 6.283185307179586, 0},    {"cos [-7,7)", 3, -7.0, 7.0, 0},
       {"cos bits [2^-30,0.9)", 3, 0x1p-30, 0.9, 1},      {"cos [0,1e5)", 3, 0.0, 1e5, 0},
+      {"sin_and_cos [0,2pi)", 4, 0.0, 6.283185307179586, 0}, {"sin_and_cos [-7,7)", 4, -7.0, 7.0, 0},
+      {"sin_and_cos bits [2^-30,0.9)", 4, 0x1p-30, 0.9, 1},  {"sin_and_cos [0,1e5)", 4, 0.0, 1e5, 0},
+      {"sin_and_cos [0.8,2.5)", 4, 0.8, 2.5, 0},
 #endif
   };
   int rc = 0;

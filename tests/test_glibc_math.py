@@ -19,6 +19,8 @@ CASES = [  # (what, lo, hi, mode)  what: 0 log, 1 sincos, 2 sin, 3 cos; mode 1 =
     (1, 0.0, 2 * np.pi, 0), (1, -7.0, 7.0, 0), (1, 2.0 ** -30, 0.9, 1), (1, 0.0, 1e5, 0), (1, 0.8, 2.5, 0),
     (2, 0.0, 2 * np.pi, 0), (2, -7.0, 7.0, 0), (2, 2.0 ** -30, 0.9, 1), (2, 0.0, 1e5, 0),
     (3, 0.0, 2 * np.pi, 0), (3, -7.0, 7.0, 0), (3, 2.0 ** -30, 0.9, 1), (3, 0.0, 1e5, 0),
+    # 4: the converged sin_and_cos pair against two separate libm calls
+    (4, 0.0, 2 * np.pi, 0), (4, -7.0, 7.0, 0), (4, 2.0 ** -30, 0.9, 1), (4, 0.0, 1e5, 0), (4, 0.8, 2.5, 0),
 ]
 
 
@@ -68,6 +70,9 @@ def test_device_math_equals_libm():
     assert np.array_equal(c.view(np.uint64), wc.view(np.uint64))
     assert np.array_equal(capi.device_math(2, x)[0].view(np.uint64), ws.view(np.uint64))
     assert np.array_equal(capi.device_math(3, x)[0].view(np.uint64), wc.view(np.uint64))
+    s, c = capi.device_math(5, x)  # the converged (sin, cos) pair of Direction(d, mu, phi)
+    assert np.array_equal(s.view(np.uint64), ws.view(np.uint64))
+    assert np.array_equal(c.view(np.uint64), wc.view(np.uint64))
 
 
 @pytest.mark.gpu
