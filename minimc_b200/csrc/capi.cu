@@ -474,8 +474,12 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
         o.rank = static_cast<uint32_t>(q.rank);
         o.off_cdf = b.add(q.cdf, q.n_cdf);
         o.off_T = b.add(q.temperature, q.n_temperature);
-        o.off_cdf_modes = b.add(q.cdf_modes, q.n_cdf * q.rank);
-        o.off_S = b.add(q.singular_values, q.rank);
+        // S[r] * CDF_modes[cdf][r]: the first product of Evaluate's left-to-right expression
+        // (ThermalScattering.cpp:199-204,241-246), one IEEE multiply (this file is built with -ffp-contract=off)
+        std::vector<double> scaled(q.n_cdf * q.rank);
+        for (uint64_t c = 0; c < q.n_cdf; c++)
+          for (uint64_t r = 0; r < q.rank; r++) scaled[c * q.rank + r] = q.singular_values[r] * q.cdf_modes[c * q.rank + r];
+        o.off_scaled_cdf_modes = b.add(scaled.data(), scaled.size());
         o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
         o.grid_begin = static_cast<uint32_t>(concatenated.size());
         concatenated.insert(concatenated.end(), q.grid, q.grid + q.n_grid);
@@ -508,8 +512,11 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
           tt.rank = static_cast<uint32_t>(t.rank);
           tt.off_E = b.add(t.energy, t.n_energy);
           tt.off_T = b.add(t.temperature, t.n_temperature);
-          tt.off_xs_E = b.add(t.xs_E, t.n_energy * t.rank);
-          tt.off_xs_S = b.add(t.xs_S, t.rank);
+          // S[r] * scatter_xs_E[E][r]: the first product of EvaluateInelastic (ThermalScattering.cpp:264-267)
+          std::vector<double> xs_SE(t.n_energy * t.rank);
+          for (uint64_t e = 0; e < t.n_energy; e++)
+            for (uint64_t r = 0; r < t.rank; r++) xs_SE[e * t.rank + r] = t.xs_S[r] * t.xs_E[e * t.rank + r];
+          tt.off_xs_SE = b.add(xs_SE.data(), xs_SE.size());
           tt.off_xs_T = b.add(t.xs_T, t.n_temperature * t.rank);
           std::vector<double> Es, betas;
           tt.n_beta_partitions = t.n_beta_partitions;

@@ -75,8 +75,8 @@ struct TslPartition {
   uint32_t n_cdf, n_grid, n_T, rank;
   uint32_t off_cdf;        // double[n_cdf]
   uint32_t off_T;          // double[n_T]
-  uint32_t off_cdf_modes;  // double[n_cdf][rank]
-  uint32_t off_S;          // double[rank]
+  uint32_t off_scaled_cdf_modes;  // double[n_cdf][rank]: S[r] * CDF_modes[cdf][r] (the reference's first product)
+  uint32_t pad0;
   uint32_t off_modes;      // double[n_grid][n_T][rank]
   uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
   uint32_t pad[2];
@@ -86,7 +86,7 @@ struct TslPartition {
 struct TslTable {
   Table1D majorant;
   uint32_t n_E, n_T, rank, pad0;
-  uint32_t off_E, off_T, off_xs_E, off_xs_S, off_xs_T;
+  uint32_t off_E, off_T, off_xs_SE, pad2, off_xs_T;  // off_xs_SE: double[n_E][rank] = S[r] * scatter_xs_E[E][r]
   uint32_t n_beta_partitions, n_alpha_partitions;
   uint32_t off_beta_partitions, off_alpha_partitions;  // TslPartition[]
   uint32_t n_Es, off_Es;        // concatenated incident energies of the beta partitions (ThermalScattering::Es)
