@@ -252,6 +252,7 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, kernel_ms = t.tolist()
+    launches_per_step = drv.last_launches
     c = dict(zip([n for n, _ in capi.Counters._fields_], counters.tolist()))
     assert c["n_histories"] == total_histories, (c["n_histories"], total_histories)
     assert c["n_lost"] == 0 and c["n_physics_errors"] == 0 and c["n_capacity_overflow"] == 0, c
@@ -283,7 +284,7 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
     launch_s = kernel_ms * 1e-3 / steps
     achieved = bytes_per_launch / launch_s / 1e9
     result = {
-        "value": value, "ms_per_step": step_ms / steps, "clocks": clocks,
+        "value": value, "ms_per_step": step_ms / steps, "clocks": clocks, "launches_per_step": launches_per_step,
         "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -345,7 +346,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": main["value"], "unit": "histories/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": main["config"], "clocks": main["clocks"],
-            "e2e": main["e2e"], "gpu_launches": args.steps, "roofline": main["roofline"],
+            "e2e": main["e2e"], "gpu_launches": args.steps * main["launches_per_step"], "roofline": main["roofline"],
             "counters_per_step": main["counters_per_step"],
         }
         if "cpu_baseline" in main:

@@ -229,6 +229,13 @@ typedef struct mmc_event_record {
 
 typedef struct mmc_world mmc_world; /* opaque: owns the device copy of the tables */
 
+/* How the histories of a fixed-source run are scheduled on the device (results are identical either way).
+ * FUSED: one persistent kernel, a particle stays in registers from birth to death (multigroup worlds always).
+ * EVENT: event-split -- particle state in HBM, one flight kernel + one S(a,b) kernel per event, live particles
+ *        stream-compacted in between (continuous-energy worlds; the default for them).  The device variant of the
+ *        call then synchronises the stream every few passes to read the number of live histories. */
+typedef enum mmc_schedule { MMC_SCHEDULE_AUTO = 0, MMC_SCHEDULE_FUSED = 1, MMC_SCHEDULE_EVENT = 2 } mmc_schedule;
+
 /* Optional knobs; zero-initialise for defaults. */
 typedef struct mmc_run_options {
   uint32_t struct_size;             /* sizeof(mmc_run_options) */
@@ -238,8 +245,10 @@ typedef struct mmc_run_options {
   uint32_t secondary_capacity;      /* per-history fission queue slots (default 64) */
   uint32_t pending_capacity;        /* per-history distinct scored bins (default 32) */
   uint32_t blocks_per_sm;           /* 0 = library default */
-  uint32_t threads_per_block;       /* 0 = library default */
+  uint32_t schedule;                /* mmc_schedule; 0 = library default */
   void* stream;                     /* cudaStream_t; NULL = the library's own stream */
+  uint32_t event_slots;             /* MMC_SCHEDULE_EVENT: histories in flight at once (0 = library default) */
+  uint32_t reserved;
 } mmc_run_options;
 
 int mmc_abi_version(void);
@@ -255,6 +264,9 @@ void mmc_world_destroy(mmc_world* world);
 
 /* Bytes of flattened tables resident on the device for this world (what mmc_world_create copied host -> device). */
 uint64_t mmc_world_bytes(const mmc_world* world);
+
+/* Kernels launched by the last mmc_fixed_source_run[_device] on this world (1 for the fused schedule). */
+uint64_t mmc_world_last_launches(const mmc_world* world);
 
 /* Total number of bins of estimator e = cosine.n_bins * energy.n_bins
  * (ParticleBins::size, Bins.cpp:192-194). */
@@ -391,6 +403,8 @@ int mmc_driver_run_device(mmc_driver* driver, uint64_t first_history, uint64_t n
 /* Drops the device copy of the World, so that the next Solve() uploads the tables again; and its size in bytes. */
 void mmc_driver_release_device(mmc_driver* driver);
 uint64_t mmc_driver_table_bytes(mmc_driver* driver);
+/* Kernels launched by the driver's last Solve() / run_device on this rank (mmc_world_last_launches). */
+uint64_t mmc_driver_last_launches(mmc_driver* driver);
 /* Parity hook: mmc_trace_histories for histories [first, first + n) of a fixed-source deck. */
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records);

@@ -90,8 +90,11 @@ class RunOptions(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("tracking", C.c_int32), ("rng_mode", C.c_int32),
         ("secondary_capacity", C.c_uint32), ("pending_capacity", C.c_uint32), ("blocks_per_sm", C.c_uint32),
-        ("threads_per_block", C.c_uint32), ("stream", C.c_void_p),
+        ("schedule", C.c_uint32), ("stream", C.c_void_p), ("event_slots", C.c_uint32), ("reserved", C.c_uint32),
     ]
+
+
+SCHEDULE_AUTO, SCHEDULE_FUSED, SCHEDULE_EVENT = 0, 1, 2  # mmc_schedule
 
 
 # every symbol include/minimc_b200.h declares
@@ -106,6 +109,7 @@ EXPORTS = (
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
     "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
+    "mmc_world_last_launches", "mmc_driver_last_launches",
 )
 
 _lib = None
@@ -209,6 +213,9 @@ def load() -> C.CDLL:
     lib.mmc_driver_table_bytes.argtypes = [C.c_void_p]
     lib.mmc_world_bytes.restype = C.c_uint64
     lib.mmc_world_bytes.argtypes = [C.c_void_p]
+    for fn in (lib.mmc_world_last_launches, lib.mmc_driver_last_launches):
+        fn.restype = C.c_uint64
+        fn.argtypes = [C.c_void_p]
     lib.mmc_driver_keff.restype = C.c_int
     lib.mmc_driver_keff.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t)]
     if lib.mmc_abi_version() != ABI_VERSION:
@@ -360,7 +367,7 @@ class World:
             pass
 
     @staticmethod
-    def _options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream):
+    def _options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream, schedule=0, event_slots=0):
         o = RunOptions()
         o.struct_size = C.sizeof(RunOptions)
         o.device = -1
@@ -370,17 +377,19 @@ class World:
         o.pending_capacity = pending_capacity
         o.blocks_per_sm = blocks_per_sm
         o.stream = stream
+        o.schedule = schedule
+        o.event_slots = event_slots
         return o
 
     def fixed_source_run(self, source: SourceDesc, estimators: Estimators, seed0: int, first_history: int,
                          n_histories: int, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0,
-                         blocks_per_sm=0, scores=None, square_scores=None):
+                         blocks_per_sm=0, scores=None, square_scores=None, schedule=0, event_slots=0):
         """mmc_fixed_source_run with host buffers.  Returns (scores, square_scores, counters dict)."""
         nb = max(estimators.total_bins, 1)
         scores = np.zeros(nb) if scores is None else scores
         square_scores = np.zeros(nb) if square_scores is None else square_scores
         counters = Counters()
-        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, None)
+        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, None, schedule, event_slots)
         check(load().mmc_fixed_source_run(
             self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
             C.byref(o), _ptr(scores, C.c_double), _ptr(square_scores, C.c_double), C.byref(counters)))
@@ -388,9 +397,9 @@ class World:
 
     def fixed_source_run_device(self, source, estimators, seed0, first_history, n_histories, d_scores, d_square,
                                 d_counters, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0,
-                                blocks_per_sm=0, stream=None):
-        """mmc_fixed_source_run_device: raw device pointers (ints), asynchronous on `stream`."""
-        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream)
+                                blocks_per_sm=0, stream=None, schedule=0, event_slots=0):
+        """mmc_fixed_source_run_device: raw device pointers (ints), on `stream`."""
+        o = self._options(tracking, secondary_capacity, pending_capacity, blocks_per_sm, stream, schedule, event_slots)
         check(load().mmc_fixed_source_run_device(
             self._handle, C.byref(source), estimators.array, estimators.n, seed0, first_history, n_histories,
             C.byref(o), d_scores, d_square, d_counters))
@@ -464,7 +473,8 @@ class Driver:
     def total_bins(self) -> int:
         return int(load().mmc_driver_total_bins(self._handle))
 
-    def set_options(self, *, device=-1, secondary_capacity=0, pending_capacity=0, blocks_per_sm=0, rng_mode=RNG_MINSTD_COMPAT):
+    def set_options(self, *, device=-1, secondary_capacity=0, pending_capacity=0, blocks_per_sm=0, rng_mode=RNG_MINSTD_COMPAT,
+                    schedule=0, event_slots=0):
         o = RunOptions()
         o.struct_size = C.sizeof(RunOptions)
         o.device = device
@@ -472,6 +482,8 @@ class Driver:
         o.secondary_capacity = secondary_capacity
         o.pending_capacity = pending_capacity
         o.blocks_per_sm = blocks_per_sm
+        o.schedule = schedule
+        o.event_slots = event_slots
         check(load().mmc_driver_set_options(self._handle, C.byref(o)))
 
     def set_shard(self, rank: int, world_size: int):
@@ -523,6 +535,10 @@ class Driver:
     @property
     def table_bytes(self) -> int:
         return int(load().mmc_driver_table_bytes(self._handle))
+
+    @property
+    def last_launches(self) -> int:
+        return int(load().mmc_driver_last_launches(self._handle))
 
     def trace(self, first_history: int, n_histories: int, cap=1 << 18):
         records = (EventRecord * cap)()

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -19,6 +21,8 @@
 using namespace mmc;
 
 namespace {
+
+constexpr uint32_t kDefaultEventSlots = 1u << 21;  // histories in flight in the event-split schedule (measured choice)
 
 thread_local std::string g_error;
 
@@ -83,6 +87,11 @@ struct mmc_world {
   double* d_bounds = nullptr;
   size_t bounds_bytes = 0;
   unsigned long long* d_next = nullptr;
+  // event-split schedule: SoA particle state, queues, counter replicas (one allocation), pinned queue counts
+  char* d_event = nullptr;
+  size_t event_bytes = 0;
+  unsigned int* h_event_counts = nullptr;
+  uint64_t last_launches = 0;  // kernels launched by the last event-split run
   // k-eigenvalue scratch
   BankSite* d_unordered = nullptr;
   size_t unordered_bytes = 0;
@@ -267,6 +276,8 @@ struct Prepared {
   std::vector<double> bounds;
   LaunchConfig cfg{};
   cudaStream_t stream = nullptr;
+  bool event_schedule = false;  // event-split kernels (event_loop.cu) instead of the fused kernel
+  uint32_t event_slots = 0;     // histories in flight at once
 };
 
 int prepare_run(
@@ -353,6 +364,91 @@ int prepare_run(
   chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 32), 2048);
   run.chunk = static_cast<uint32_t>(chunk);
   out.stream = opt.stream ? static_cast<cudaStream_t>(opt.stream) : w->stream;
+  // schedule: continuous-energy fixed-source runs default to the event-split kernels
+  uint32_t schedule = opt.schedule, slots = opt.event_slots;
+  if (const char* env = std::getenv("MMC_SCHEDULE")) {  // development override, for A/B measurements
+    if (schedule == MMC_SCHEDULE_AUTO) schedule = static_cast<uint32_t>(std::atoi(env));
+  }
+  if (const char* env = std::getenv("MMC_EVENT_SLOTS")) {
+    if (slots == 0) slots = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
+  }
+  if (schedule > MMC_SCHEDULE_EVENT) return fail(MMC_ERR_INVALID, "unknown schedule %u", schedule);
+  if (schedule == MMC_SCHEDULE_EVENT && (!continuous_energy || generation || trace))
+    return fail(MMC_ERR_INVALID, "MMC_SCHEDULE_EVENT is for continuous-energy fixed-source runs");
+  out.event_schedule = continuous_energy && !generation && !trace && schedule != MMC_SCHEDULE_FUSED;
+  if (out.event_schedule) {
+    if (slots == 0) slots = kDefaultEventSlots;
+    // worlds with fission keep a secondary deque per slot: bound its memory
+    if (w->has_fission) slots = std::min<uint32_t>(slots, 1u << 18);
+    out.event_slots = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(n_histories, 1), slots));
+  }
+  return MMC_OK;
+}
+
+// Carves the event-split schedule's device buffers out of one allocation.
+struct EventBuffers {
+  EventState st{};
+  EventQueues q{};
+  unsigned long long* counter_replicas = nullptr;
+};
+
+int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
+  const size_t n = event_padded_slots(n_slots);  // keeps every array 128-byte aligned
+  const size_t need = n * (kEventStateBytesPerSlot + 3 * sizeof(uint32_t)) + 256 +
+                      kCounterReplicas * sizeof(mmc_counters);
+  if (need > w->event_bytes) {
+    if (w->d_event) cudaFree(w->d_event);
+    w->d_event = nullptr;
+    w->event_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_event, need));
+    w->event_bytes = need;
+  }
+  if (!w->h_event_counts) MMC_CUDA(cudaMallocHost(&w->h_event_counts, 4 * sizeof(unsigned int)));
+  char* at = w->d_event;
+  auto take = [&](auto*& ptr, size_t bytes) {
+    ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(at);
+    at += bytes;
+  };
+  EventState& st = out.st;
+  take(st.px, n * 8), take(st.py, n * 8), take(st.pz, n * 8);
+  take(st.dx, n * 8), take(st.dy, n * 8), take(st.dz, n * 8);
+  take(st.energy, n * 8), take(st.tsl_T, n * 8);
+  take(st.rng, n * 4), take(st.cell, n * 4), take(st.surface, n * 4), take(st.event, n * 4);
+  take(st.n_pending, n * 4), take(st.dq_head, n * 4), take(st.dq_count, n * 4), take(st.tsl_off, n * 4);
+  take(out.q.alive[0], n * 4), take(out.q.alive[1], n * 4), take(out.q.tsl, n * 4);
+  take(out.q.count, 256);
+  take(out.counter_replicas, kCounterReplicas * sizeof(mmc_counters));
+  return MMC_OK;
+}
+
+// The pass loop of the event-split schedule.  One pass = one event of every live history (flight kernel + S(a,b)
+// kernel).  The number of live slots is read back every few passes: it bounds the next launches' grids and ends the
+// loop.  Passes over an empty queue are no-ops, so checking late is harmless.
+int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_scores, unsigned long long* d_square,
+                       mmc_counters* d_counters) {
+  EventBuffers b;
+  if (int s = ensure_event_buffers(w, p.event_slots, b)) return s;
+  if (int s = ensure_scratch(w, p.event_slots, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
+  if (!p.bounds.empty())
+    MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), p.stream));
+  EventTslConfig tsl;
+  MMC_CUDA(configure_event_tsl(w->header.sc_arena_bytes, w->smem_optin, static_cast<uint32_t>(w->sm_count), tsl));
+  MMC_CUDA(launch_event_init(b.st, b.q, p.event_slots, b.counter_replicas, p.stream));
+  uint32_t alive = p.event_slots, pass = 0;
+  w->last_launches = 1;
+  while (alive) {
+    const int batch = 8;
+    for (int k = 0; k < batch; k++, pass++)
+      MMC_CUDA(launch_event_pass(w->d_blob, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next,
+                                 d_scores, d_square, b.counter_replicas, tsl, p.stream));
+    w->last_launches += 2 * batch;
+    MMC_CUDA(cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream));
+    MMC_CUDA(cudaStreamSynchronize(p.stream));
+    alive = w->h_event_counts[pass & 1u];
+  }
+  MMC_CUDA(launch_event_finish(b.counter_replicas, d_counters, p.stream));
+  w->last_launches += 1;
   return MMC_OK;
 }
 
@@ -396,6 +492,8 @@ int mmc_device_count(void) {
 }
 
 uint64_t mmc_world_bytes(const mmc_world* world) { return world ? world->blob_bytes : 0; }
+
+uint64_t mmc_world_last_launches(const mmc_world* world) { return world ? world->last_launches : 0; }
 
 uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
   if (!e) return 0;
@@ -463,7 +561,33 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
       }
       return out;
     };
-    auto partitions = [&b](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
+    // the scaled CDF modes of every partition first, back to back (WorldHeader::off_sc_arena):
+    // S[r] * CDF_modes[cdf][r] is the first product of Evaluate's left-to-right expression
+    // (ThermalScattering.cpp:199-204,241-246), one IEEE multiply (this file is built with -ffp-contract=off)
+    std::vector<uint32_t> sc_offsets;
+    size_t sc_next = 0;
+    {
+      b.pad();
+      h.off_sc_arena = static_cast<uint32_t>(b.bytes.size());
+      auto add_scaled = [&](const mmc_tsl_partition* p, int n) {
+        for (int i = 0; i < n; i++) {
+          const mmc_tsl_partition& q = p[i];
+          std::vector<double> scaled(q.n_cdf * q.rank);
+          for (uint64_t c = 0; c < q.n_cdf; c++)
+            for (uint64_t r = 0; r < q.rank; r++) scaled[c * q.rank + r] = q.singular_values[r] * q.cdf_modes[c * q.rank + r];
+          sc_offsets.push_back(b.add(scaled.data(), scaled.size()));
+        }
+      };
+      for (int n = 0; n < d->n_nuclides; n++)
+        for (int r = 0; r < d->ce->nuclides[n].n_reactions; r++)
+          if (const mmc_tsl_desc* t = d->ce->nuclides[n].reactions[r].tsl) {
+            add_scaled(t->beta_partitions, t->n_beta_partitions);
+            add_scaled(t->alpha_partitions, t->n_alpha_partitions);
+          }
+      b.pad();
+      h.sc_arena_bytes = static_cast<uint32_t>(b.bytes.size()) - h.off_sc_arena;
+    }
+    auto partitions = [&b, &sc_offsets, &sc_next](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
       std::vector<TslPartition> out(n);
       for (int i = 0; i < n; i++) {
         const mmc_tsl_partition& q = p[i];
@@ -474,12 +598,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
         o.rank = static_cast<uint32_t>(q.rank);
         o.off_cdf = b.add(q.cdf, q.n_cdf);
         o.off_T = b.add(q.temperature, q.n_temperature);
-        // S[r] * CDF_modes[cdf][r]: the first product of Evaluate's left-to-right expression
-        // (ThermalScattering.cpp:199-204,241-246), one IEEE multiply (this file is built with -ffp-contract=off)
-        std::vector<double> scaled(q.n_cdf * q.rank);
-        for (uint64_t c = 0; c < q.n_cdf; c++)
-          for (uint64_t r = 0; r < q.rank; r++) scaled[c * q.rank + r] = q.singular_values[r] * q.cdf_modes[c * q.rank + r];
-        o.off_scaled_cdf_modes = b.add(scaled.data(), scaled.size());
+        o.off_scaled_cdf_modes = sc_offsets[sc_next++];  // in the arena, same traversal order
         o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
         o.grid_begin = static_cast<uint32_t>(concatenated.size());
         concatenated.insert(concatenated.end(), q.grid, q.grid + q.n_grid);
@@ -572,6 +691,8 @@ void mmc_world_destroy(mmc_world* w) {
   cudaFree(w->d_pending);
   cudaFree(w->d_bounds);
   cudaFree(w->d_next);
+  cudaFree(w->d_event);
+  if (w->h_event_counts) cudaFreeHost(w->h_event_counts);
   cudaFree(w->d_unordered);
   cudaFree(w->d_child_count);
   cudaFree(w->d_child_start);
@@ -590,6 +711,10 @@ int mmc_fixed_source_run_device(
   if (p.run.total_bins && (!d_scores || !d_square_scores)) return fail(MMC_ERR_INVALID, "tally buffers are NULL");
   MMC_CUDA(cudaSetDevice(w->device));
   if (n_histories == 0) return MMC_OK;
+  if (p.event_schedule)
+    return run_event_schedule(w, p, reinterpret_cast<unsigned long long*>(d_scores),
+                              reinterpret_cast<unsigned long long*>(d_square_scores), d_counters);
+  w->last_launches = 1;
   const size_t threads = static_cast<size_t>(p.cfg.blocks) * kThreadsPerBlock;
   if (int s = ensure_scratch(w, threads, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
   if (!p.bounds.empty())

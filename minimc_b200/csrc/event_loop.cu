@@ -1,0 +1,386 @@
+// Event-split schedule of the history loop for continuous-energy worlds (sm_100a).
+//
+// The fused kernel (kernels.cu) keeps a particle in registers for its whole life.
+// For the S(a,b) decks that puts ~14 k instructions (230 KB) of divergent code in
+// one kernel: ncu shows warps waiting on instruction fetch as often as on memory.
+// Here one PASS advances every live history by one event with two small kernels:
+//
+//   event_flight_kernel   refill (next secondary / next history, Source::Sample), cross-section lookup,
+//                         distance to collision and to the nearest surface, crossing or collision, reaction
+//                         choice, tallies.  A collision that chose thermal scattering is not sampled here:
+//                         its slot goes to the S(a,b) queue.
+//   event_tsl_kernel      ThermalScattering::Scatter (SampleBeta, SampleAlpha, Particle::Scatter) for the
+//                         queued slots -- every lane of every warp runs the POD sampler.
+//
+// Particle state streams through HBM as structure-of-arrays (EventState, kernels.h) indexed by SLOT; a slot is one
+// history context (current particle, pending-score table, secondary deque), so the per-history bookkeeping of
+// FixedSource.cpp:48-72 stays slot-local exactly as it is lane-local in the fused kernel.  Between kernels the live
+// slots and the S(a,b) slots are stream-compacted: ballot + popc inside a warp, the eight warp totals scanned in
+// shared memory, ONE global atomic per CTA and queue, order inside a CTA preserved.  The arithmetic per particle is
+// the same device code (transport.cuh, physics_ce.cuh) in the same order, so results stay bit-identical to the
+// fused kernel and to the reference; tallies are integer sums and do not depend on the schedule.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kernel_common.cuh"
+
+#ifndef MMC_EV_FLIGHT_BLOCKS
+#define MMC_EV_FLIGHT_BLOCKS 3
+#endif
+#ifndef MMC_EV_TSL_THREADS
+#define MMC_EV_TSL_THREADS 768  // one persistent CTA per SM
+#endif
+
+namespace mmc {
+
+namespace {
+
+constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
+constexpr int kTslThreads = MMC_EV_TSL_THREADS;
+constexpr size_t kTslRowBytes = 10 * kTslThreads * sizeof(double2);
+
+// exclusive prefix of this warp among the CTA's warp totals, and the CTA total
+__device__ __forceinline__ uint32_t warp_prefix(const uint32_t* totals, uint32_t warp, uint32_t& block_total) {
+  uint32_t prefix = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < kWarpsPerBlock; k++) {
+    const uint32_t v = totals[k];
+    if (static_cast<uint32_t>(k) < warp) prefix += v;
+    total += v;
+  }
+  block_total = total;
+  return prefix;
+}
+
+__global__ void event_init_kernel(const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
+                                  uint32_t n_slots, uint32_t n_padded, unsigned long long* counter_replicas) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slots) {
+    st.event[i] = MMC_EV_CAPTURE;  // "dead": the first pass refills every slot
+    st.n_pending[i] = 0;
+    st.dq_head[i] = 0;
+    st.dq_count[i] = 0;
+  }
+  if (i < n_padded) {  // queue entries past the end must still be valid slots (event_flight_kernel reads them)
+    q.alive[0][i] = i < n_slots ? i : 0u;
+    q.alive[1][i] = 0;
+  }
+  if (i < kCounterReplicas * kNumCounters) counter_replicas[i] = 0;
+  if (i == 0) {
+    q.count[0] = n_slots;
+    q.count[1] = q.count[2] = q.count[3] = 0;
+  }
+}
+
+template <int kTracking>
+__global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_flight_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
+    const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
+    BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
+    unsigned long long* scores, unsigned long long* square_scores, unsigned long long* counter_replicas) {
+  __shared__ uint32_t s_totals[3][kWarpsPerBlock];  // per-warp counts: history claims, live slots, S(a,b) slots
+  __shared__ unsigned long long s_claim_base;
+  __shared__ uint32_t s_queue_base[2];
+  __shared__ uint32_t s_counters[kNumCounters];
+
+  const uint32_t parity = pass & 1u;
+  const uint32_t first = blockIdx.x * kThreadsPerBlock;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t i = first + threadIdx.x;
+  // Two dependent round trips to HBM instead of four: the queue entry is read together with the queue length (the
+  // queues are zero-filled past their end, so a stale entry is a valid slot), and the whole particle together with
+  // the slot's event code (a dead slot's particle is loaded in vain: 4 % of the slots in a steady-state pass).
+  const uint32_t slot = q.alive[parity][i];
+  const uint32_t n = q.count[parity];
+  Particle p;
+  p.event = st.event[slot];
+  p.px = st.px[slot], p.py = st.py[slot], p.pz = st.pz[slot];
+  p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
+  p.energy = st.energy[slot];
+  p.group = 0;
+  p.rng.x = st.rng[slot];
+  p.cell = st.cell[slot];
+  p.surface = st.surface[slot];
+  if (first >= n) return;  // CTA-uniform
+  if (threadIdx.x < kNumCounters) s_counters[threadIdx.x] = 0;
+  const bool valid = i < n;
+  const WorldView w(world_g);
+  const bool has_secondaries = run.secondary_capacity > 1;
+
+  if (!valid) p.event = MMC_EV_CAPTURE;
+  bool alive = valid && is_alive(p.event);
+  SiteDeque dq;
+  dq.slots = site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
+  dq.mask = run.secondary_capacity - 1;
+  dq.head = 0;
+  dq.count = 0;
+  if (valid && has_secondaries) {
+    dq.head = st.dq_head[slot];
+    dq.count = st.dq_count[slot];
+  }
+  uint32_t n_pending = (valid && run.n_estimators) ? st.n_pending[slot] : 0u;
+  ThreadCounters c;
+
+  // ---- refill: next particle of the slot's history (bank.back(), FixedSource.cpp:63-71) ...
+  if (valid && !alive && dq.count) {
+    dq.count--;
+    load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
+    alive = true;
+    c.births++;
+  }
+  // ... else a new history: one atomic per CTA claims the indices
+  const bool need = valid && !alive;
+  const unsigned need_mask = __ballot_sync(kFull, need);
+  if (lane == 0) s_totals[0][warp] = __popc(need_mask);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int k = 0; k < kWarpsPerBlock; k++) total += s_totals[0][k];
+    unsigned long long base = 0;
+    if (total) {
+      base = *reinterpret_cast<volatile unsigned long long*>(next_history);
+      if (base < run.n_histories) base = atomicAdd(next_history, static_cast<unsigned long long>(total));
+    }
+    s_claim_base = base;
+  }
+  __syncthreads();
+  bool retired = false;
+  if (need) {
+    uint32_t total;
+    const uint64_t idx = s_claim_base + warp_prefix(s_totals[0], warp, total) + __popc(need_mask & lanes_below);
+    if (idx < run.n_histories) {
+      // a new scoring proxy starts empty: FixedSource.cpp:48
+      n_pending = 0;
+      sample_source(run.source, run.seed0 + run.first_history + idx, p);
+      alive = true;
+      c.histories++;
+      c.births++;
+    } else {
+      retired = true;  // no work left for this slot
+    }
+  }
+
+  // ---- one event
+  StepOut o;
+  o.secondaries = 0;
+  o.need_direction = false;
+  o.need_tsl = false;
+  o.error_physics = o.error_capacity = o.error_lost = false;
+  if (alive) {
+    if (p.cell < 0) {
+      // TransportMethod.cpp:55: p.SetCell(w.FindCellContaining(p.GetPosition()))
+      p.cell = find_cell(w, p.px, p.py, p.pz);
+      if (p.cell < 0) {
+        o.error_lost = true;
+        p.event = MMC_EV_LEAK;
+      }
+    }
+    if (p.cell >= 0) transport_step<kTracking, true, false, true>(w, p, dq, o);
+    count_event(c, p, o);
+  }
+
+  // ---- EstimatorSetProxy::Score(p): TransportMethod.cpp:74 (see kernels.cu for the incremental commit)
+  uint2* pending = pending_scratch + static_cast<size_t>(slot) * run.pending_capacity;
+  for (int32_t e = 0; e < run.n_estimators; e++) {
+    uint64_t bin = 0;
+    const bool hit = alive && !o.error_lost && estimator_score<true>(run.estimators[e], bounds, p, bin);
+    const unsigned hit_mask = __ballot_sync(kFull, hit);
+    if (hit) {
+      uint32_t k = 0, s = 0;
+      for (; s < n_pending; s++)
+        if (pending[s].x == static_cast<uint32_t>(bin)) break;
+      if (s < n_pending) {
+        k = pending[s].y;
+        pending[s].y = k + 1;
+      } else if (n_pending < run.pending_capacity) {
+        pending[n_pending++] = make_uint2(static_cast<uint32_t>(bin), 1u);
+      } else {
+        c.capacity++;
+      }
+      c.scores++;
+      const unsigned peers = __match_any_sync(hit_mask, bin);
+      const uint32_t sq = __reduce_add_sync(peers, 2u * k + 1u);
+      if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
+        atomicAdd(scores + bin, static_cast<unsigned long long>(__popc(peers)));
+        atomicAdd(square_scores + bin, static_cast<unsigned long long>(sq));
+      }
+    }
+  }
+
+  // ---- state back to HBM
+  if (alive) {
+    st.px[slot] = p.px, st.py[slot] = p.py, st.pz[slot] = p.pz;
+    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
+    st.energy[slot] = p.energy;
+    st.rng[slot] = p.rng.x;
+    st.cell[slot] = p.cell;
+    st.surface[slot] = p.surface;
+    st.event[slot] = p.event;
+    if (run.n_estimators) st.n_pending[slot] = n_pending;
+    if (has_secondaries) {
+      st.dq_head[slot] = dq.head;
+      st.dq_count[slot] = dq.count;
+    }
+    if (o.need_tsl) {
+      st.tsl_T[slot] = o.tsl_T;
+      st.tsl_off[slot] = o.tsl_off;
+    }
+  }
+
+  // ---- stream compaction: slots that still have work, and slots awaiting S(a,b) sampling
+  const bool keep = valid && !retired;
+  const bool to_tsl = alive && o.need_tsl;
+  const unsigned keep_mask = __ballot_sync(kFull, keep);
+  const unsigned tsl_mask = __ballot_sync(kFull, to_tsl);
+  if (lane == 0) {
+    s_totals[1][warp] = __popc(keep_mask);
+    s_totals[2][warp] = __popc(tsl_mask);
+  }
+  // ---- counters: warp sums into shared memory
+  {
+    const uint32_t v[kNumCounters] = {c.histories, c.births,      c.events, c.collisions, c.crossings, c.virtuals,
+                                      c.scores,    c.secondaries, c.banked, c.lost,       c.capacity,  c.physics};
+#pragma unroll
+    for (int k = 0; k < kNumCounters; k++) {
+      const uint32_t sum = __reduce_add_sync(kFull, v[k]);
+      if (lane == 0 && sum) atomicAdd(&s_counters[k], sum);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t keep_total = 0, tsl_total = 0;
+    for (int k = 0; k < kWarpsPerBlock; k++) keep_total += s_totals[1][k], tsl_total += s_totals[2][k];
+    s_queue_base[0] = keep_total ? atomicAdd(&q.count[parity ^ 1u], keep_total) : 0u;
+    s_queue_base[1] = tsl_total ? atomicAdd(&q.count[2u + parity], tsl_total) : 0u;
+  }
+  if (threadIdx.x < kNumCounters && s_counters[threadIdx.x])
+    atomicAdd(counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters + threadIdx.x,
+              static_cast<unsigned long long>(s_counters[threadIdx.x]));
+  __syncthreads();
+  uint32_t total;
+  if (keep) q.alive[parity ^ 1u][s_queue_base[0] + warp_prefix(s_totals[1], warp, total) + __popc(keep_mask & lanes_below)] = slot;
+  if (to_tsl) q.tsl[s_queue_base[1] + warp_prefix(s_totals[2], warp, total) + __popc(tsl_mask & lanes_below)] = slot;
+}
+
+// ThermalScattering::Scatter (ThermalScattering.cpp:159-171) for the slots the flight kernel queued.
+//
+// ncu on B200 (profiles/r01d_*): this kernel is bound by L1 WAVEFRONTS -- every lane gathers its own 80-byte rows,
+// so one load instruction costs up to 32 cache-line lookups -- not by fp64 issue or HBM.  Hence one persistent CTA
+// per SM with the gathered tables in shared memory: (1) each lane's two mode rows in a [pair][thread] column
+// (ce::SharedRows: 4 conflict-free wavefronts per read instead of up to 32), (2) when it fits, the arena of every
+// partition's S*CDF_modes rows (WorldHeader::off_sc_arena, 44 KB at the reference's table shapes; rows are 80 bytes
+// apart, i.e. 5 sixteen-byte bank groups -- odd -- so rows that differ modulo 8 never conflict).
+// Warps walk the queue in chunks of 32 slots; state loads and stores are coalesced over the compacted queue.
+template <bool kSharedSc>
+__global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
+    uint32_t pass, unsigned long long* counter_replicas) {
+  extern __shared__ __align__(16) char smem[];
+  double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
+  char* s_sc = smem + 10 * kTslThreads * sizeof(double2);
+  const uint32_t parity = pass & 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q.count[parity] = 0;             // the alive queue this pass consumed: the next pass appends to it
+    q.count[2u + (parity ^ 1u)] = 0; // the S(a,b) queue of the next pass
+  }
+  const uint32_t n = q.count[2u + parity];
+  constexpr uint32_t kWarps = kTslThreads / 32;
+  if (blockIdx.x * kWarps * 32u >= n) return;  // CTA-uniform: not even the first warp has work
+  const WorldView w(world_g);
+  if (kSharedSc) {
+    const uint4* src = reinterpret_cast<const uint4*>(world_g + w.h->off_sc_arena);
+    uint4* dst = reinterpret_cast<uint4*>(s_sc);
+    for (uint32_t k = threadIdx.x; k < w.h->sc_arena_bytes / 16; k += kTslThreads) dst[k] = __ldg(src + k);
+    __syncthreads();
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  ce::SharedRows<kTslThreads, kSharedSc> rows(s_rows, s_sc, w.h->off_sc_arena);
+  for (uint32_t base = (blockIdx.x * kWarps + warp) * 32u; base < n; base += gridDim.x * kWarps * 32u) {
+    const uint32_t i = base + lane;
+    if (i >= n) continue;
+    const uint32_t slot = q.tsl[i];
+    Particle p;
+    p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
+    p.energy = st.energy[slot];
+    p.rng.x = st.rng[slot];
+    const double T = st.tsl_T[slot];
+    const TslTable& t = *w.at<TslTable>(st.tsl_off[slot]);
+    bool error = false;
+    ce::tsl_scatter(w, t, p, T, error, rows);
+    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
+    st.energy[slot] = p.energy;
+    st.rng[slot] = p.rng.x;
+    if (error) {
+      // the reference throws here (-> std::terminate); the flight kernel counted the collision already
+      st.event[slot] = MMC_EV_CAPTURE;
+      unsigned long long* mine = counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters;
+      atomicAdd(mine + 3, ~0ull);  // n_collisions - 1
+      atomicAdd(mine + 11, 1ull);  // n_physics_errors + 1
+    }
+  }
+}
+
+__global__ void event_finish_kernel(const unsigned long long* counter_replicas, mmc_counters* counters) {
+  const uint32_t k = threadIdx.x;
+  if (k >= kNumCounters) return;
+  unsigned long long sum = 0;
+  for (int r = 0; r < kCounterReplicas; r++) sum += counter_replicas[r * kNumCounters + k];
+  if (sum) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + k, sum);
+}
+
+}  // namespace
+
+static_assert(sizeof(mmc_counters) == kNumCounters * sizeof(uint64_t), "mmc_counters layout");
+
+cudaError_t launch_event_init(const EventState& st, const EventQueues& q, uint32_t n_slots,
+                              unsigned long long* counter_replicas, cudaStream_t stream) {
+  const uint32_t n_padded = event_padded_slots(n_slots);
+  const uint32_t n = n_padded > kCounterReplicas * kNumCounters ? n_padded : kCounterReplicas * kNumCounters;
+  event_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st, q, n_slots, n_padded, counter_replicas);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_event_pass(
+    const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
+    uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
+    unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
+    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream) {
+  const uint32_t blocks = (alive_upper_bound + kThreadsPerBlock - 1) / kThreadsPerBlock;
+  if (blocks == 0) return cudaSuccess;
+  if (run.tracking == MMC_TRACK_CELL_DELTA)
+    event_flight_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kThreadsPerBlock, 0, stream>>>(
+        world_d, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
+        counter_replicas);
+  else
+    event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kThreadsPerBlock, 0, stream>>>(
+        world_d, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
+        counter_replicas);
+  // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queue can feed
+  const uint32_t per_cta = kTslThreads;
+  uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
+  if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
+  if (tsl.shared_sc)
+    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(world_d, st, q, pass, counter_replicas);
+  else
+    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, st, q, pass, counter_replicas);
+  return cudaGetLastError();
+}
+
+cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out) {
+  out.sm_count = sm_count;
+  out.sc_arena_bytes = sc_arena_bytes;
+  out.shared_sc = sc_arena_bytes > 0 && kTslRowBytes + sc_arena_bytes <= smem_optin;
+  cudaError_t e = cudaFuncSetAttribute(event_tsl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTslRowBytes));
+  if (e == cudaSuccess && out.shared_sc)
+    e = cudaFuncSetAttribute(event_tsl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kTslRowBytes + sc_arena_bytes));
+  return e;
+}
+
+cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream) {
+  event_finish_kernel<<<1, 32, 0, stream>>>(counter_replicas, counters);
+  return cudaGetLastError();
+}
+
+}  // namespace mmc

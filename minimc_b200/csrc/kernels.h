@@ -50,6 +50,50 @@ cudaError_t launch_test_geometry(
     const char* world_d, size_t n, const double* pos_d, const double* dir_d, int32_t* cell_d, int32_t* surface_d,
     double* distance_d, cudaStream_t stream);
 
+// ---- event-split schedule (event_loop.cu) -----------------------------------------
+// Particle state of n_slots concurrently running histories as structure-of-arrays in HBM.  A slot is one history
+// context (current particle, per-history pending-score table, secondary deque); the flight and the S(a,b) kernels
+// stream the arrays they need, coalesced over the compacted queues of slot indices.
+struct EventState {
+  double *px, *py, *pz, *dx, *dy, *dz, *energy;  // [n_slots]
+  double* tsl_T;                                 // temperature at the pending S(a,b) collision
+  uint32_t* rng;                                 // minstd_rand state
+  int32_t *cell, *surface, *event;
+  uint32_t* n_pending;                           // entries used in the slot's pending-score table
+  uint32_t *dq_head, *dq_count;                  // secondary deque (worlds with fission)
+  uint32_t* tsl_off;                             // blob offset of the TslTable of the pending S(a,b) collision
+};
+constexpr size_t kEventStateBytesPerSlot = 8 * 8 + 8 * 4;
+
+struct EventQueues {
+  uint32_t* alive[2];   // compacted slot indices, ping-pong between passes
+  uint32_t* tsl;        // slots whose collision awaits S(a,b) sampling in this pass
+  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity)
+};
+
+constexpr int kCounterReplicas = 64;
+
+// array length for n_slots slots: whole CTAs of the flight kernel may read (not use) queue entries past the end
+inline uint32_t event_padded_slots(uint32_t n_slots) { return (n_slots + 255u) & ~255u; }
+
+struct EventTslConfig {
+  uint32_t sm_count = 0;
+  uint32_t sc_arena_bytes = 0;
+  bool shared_sc = false;  // the S*CDF_modes arena fits into shared memory next to the per-lane mode rows
+};
+
+cudaError_t launch_event_init(const EventState& st, const EventQueues& q, uint32_t n_slots,
+                              unsigned long long* counter_replicas, cudaStream_t stream);
+// one pass = one event of every live slot: the flight kernel, then the S(a,b) kernel over the slots it queued
+cudaError_t launch_event_pass(
+    const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
+    uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
+    unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
+    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream);
+// shared-memory plan of the S(a,b) kernel for a world (opts the kernels into their dynamic shared memory)
+cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out);
+cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream);
+
 // occupancy query for the fused kernel
 int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem);
 

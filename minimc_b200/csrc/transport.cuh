@@ -104,7 +104,7 @@ __device__ __forceinline__ void normalize(double& x, double& y, double& z) {
 }
 
 // Direction(const Direction& d, mu, phi): Point.cpp:98-121
-__device__ __noinline__ void rotate_direction(
+static __device__ __noinline__ void rotate_direction(
     double dx, double dy, double dz, double mu, double phi, double& ox, double& oy, double& oz) {
   const bool off_xaxis = dx <= 0.9 && dx > -0.9;
   const double ax = off_xaxis ? 1.0 : 0.0, ay = off_xaxis ? 0.0 : 1.0, az = 0.0;
@@ -299,6 +299,11 @@ struct StepOut {
   bool error_physics;
   bool error_capacity;
   bool error_lost;
+  // event-split schedule (event_loop.cu): the collision chose a thermal-scattering scatter and left the S(a,b)
+  // sampling to the caller; the table's blob offset and the cell temperature at the collision site
+  bool need_tsl;
+  uint32_t tsl_off;
+  double tsl_T;
 };
 
 // Material::GetMicroscopicTotal (Material.cpp:53-62): accumulate afrac*total
@@ -441,10 +446,11 @@ namespace mmc {
 // One iteration of SurfaceTracking::Transport (TransportMethod.cpp:56-75) or
 // CellDeltaTracking::Transport (TransportMethod.cpp:92-120).  kCE selects the
 // Continuous (true) or Multigroup (false) Interaction of the world's nuclides.
-template <int kTracking, bool kCE, bool kDeferDirection = false>
+template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false>
 __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out) {
   out.secondaries = 0;
   out.need_direction = false;
+  out.need_tsl = false;
   out.error_physics = out.error_capacity = out.error_lost = false;
   const int32_t mat = w.at<int32_t>(w.h->off_cell_material)[p.cell];
   if (mat < 0) {  // born in a void cell: the reference dereferences a null Material
@@ -507,7 +513,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
     }
     stream(p, d_coll);
     if (real) {
-      if (kCE) ce::collide_continuous(w, p, mat, dq, out, ev);
+      if (kCE) ce::collide_continuous<kDeferTsl>(w, p, mat, dq, out, ev);
       else collide_multigroup<kDeferDirection>(w, p, mat, micro, dq, out);
     } else {
       p.event = MMC_EV_VIRTUAL_COLLISION;
@@ -517,7 +523,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
 
 // ------------------------------------------------------------------- tallies
 // Bins::GetIndex for each concrete type, Bins.cpp:72-82,112-123,158-162
-__device__ __noinline__ uint64_t bins_index(const BinsSpec& b, const double* bounds, double v) {
+static __device__ __noinline__ uint64_t bins_index(const BinsSpec& b, const double* bounds, double v) {
   switch (b.kind) {
   case MMC_BINS_LINSPACE:
     if (v < b.lower) return 0;

@@ -59,6 +59,9 @@ struct WorldHeader {
   uint32_t off_mg_capture, off_mg_scatter, off_mg_fission, off_mg_nubar;
   uint32_t off_mg_scatter_probs, off_mg_chi;  // double[n_nuclides][G][G]
   uint32_t off_ce_nuclides;     // CeNuclide[n_nuclides]; 0 for multigroup worlds
+  // every partition's S[r] * CDF_modes[cdf][r] array (TslPartition::off_scaled_cdf_modes), contiguous: the S(a,b)
+  // kernel of the event-split schedule stages this arena into shared memory when it fits
+  uint32_t off_sc_arena, sc_arena_bytes;
 };
 
 // ---- continuous-energy tables (blob offsets; see include/minimc_b200.h mmc_ce_desc)

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Builds a variant of libminimc_b200.so with extra nvcc defines for kernels.cu (development experiments only):
+# Builds a variant of libminimc_b200.so with extra nvcc defines for kernels.cu and event_loop.cu (development
+# experiments only):
 #   scripts/build_variant.sh NAME -DMMC_CE_BLOCKS_PER_SM=2 ...
 # -> minimc_b200/csrc/build/variants/NAME.so   (travels to the GPU box; scripts/gpu_variants.sh swaps it in there)
 set -e
@@ -7,8 +8,10 @@ cd "$(dirname "$0")/../minimc_b200/csrc"
 NAME=$1; shift
 make -s >/dev/null
 mkdir -p build/variants
-nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall "$@" \
-  -c kernels.cu -o build/variants/$NAME.kernels.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$NAME.so build/variants/$NAME.kernels.o build/capi.o build/host_*.o
-rm build/variants/$NAME.kernels.o
+FLAGS="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall"
+nvcc $FLAGS "$@" -c kernels.cu -o build/variants/$NAME.kernels.o &
+nvcc $FLAGS "$@" -Xptxas -v -c event_loop.cu -o build/variants/$NAME.event_loop.o 2>&1 | grep -A2 "event_\(flight\|tsl\)_kernel" | grep -E "Used|spill" || true
+wait
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$NAME.so build/variants/$NAME.kernels.o build/variants/$NAME.event_loop.o build/capi.o build/host_*.o
+rm build/variants/$NAME.kernels.o build/variants/$NAME.event_loop.o
 echo built build/variants/$NAME.so

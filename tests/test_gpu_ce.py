@@ -56,12 +56,20 @@ def test_ce_event_traces_match_reference_golden(tables, name, tag):
     _compare_traces(mine, ref, (name, tag) in util.CE_EXACT)
 
 
+# (schedule, event_slots): the library default (event-split for continuous energy), the fused persistent kernel, and
+# the event-split kernels with a slot count that is neither a multiple of the warp nor of the CTA, so that slots are
+# refilled many times and the compacted queues end in ragged warps
+SCHEDULES = {"default": (capi.SCHEDULE_AUTO, 0), "fused": (capi.SCHEDULE_FUSED, 0), "event_ragged": (capi.SCHEDULE_EVENT, 301)}
+
+
+@pytest.mark.parametrize("schedule", list(SCHEDULES))
 @pytest.mark.parametrize("name,tag", util.CE_CASE_IDS)
-def test_ce_tallies_match_reference_out(tables, name, tag):
+def test_ce_tallies_match_reference_out(tables, name, tag, schedule):
     drv = capi.Driver(text=_case(tables, name, tag))
-    drv.set_options(secondary_capacity=256)
+    drv.set_options(secondary_capacity=256, schedule=SCHEDULES[schedule][0], event_slots=SCHEDULES[schedule][1])
     scores, squares = drv.solve()
     c = drv.counters()
+    assert (drv.last_launches == 1) == (schedule == "fused")
     assert c["n_histories"] == util.CE_HISTORIES and c["n_lost"] == 0 and c["n_physics_errors"] == 0
     golden = (util.GOLDEN / "ce" / f"{name}__{tag}.out").read_text()
     if (name, tag) in util.CE_EXACT:
@@ -128,7 +136,9 @@ def test_ce_resample_limit_is_reported(tables):
     partition's grid makes BetaPartition::Evaluate divide 0 by 0 and the resample limit trip: the reference throws
     from a noexcept function (std::terminate); here the run reports MMC_ERR_PHYSICS."""
     text = ce_decks.slab_deck(tables, histories=2000, temperature=100.0)
-    drv = capi.Driver(text=text)
-    with pytest.raises(capi.MinimcError) as e:
-        drv.solve()
-    assert e.value.status == capi.ERR_PHYSICS
+    for schedule in (capi.SCHEDULE_FUSED, capi.SCHEDULE_EVENT):
+        drv = capi.Driver(text=text)
+        drv.set_options(schedule=schedule)
+        with pytest.raises(capi.MinimcError) as e:
+            drv.solve()
+        assert e.value.status == capi.ERR_PHYSICS
