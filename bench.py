@@ -62,12 +62,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def dram_traffic_per_launch(workload):
-    """dram__bytes_read+write per launch of the fused kernel from the committed ncu capture, if any."""
+def dram_traffic_per_step(workload, schedule, counters_per_rank):
+    """dram__bytes_read+write of one step's kernels from the committed ncu captures (profiles/traffic.json), if any:
+    a per-launch figure for the fused kernel (tables and tallies only: it does not scale with histories), a
+    per-event figure for the flight + S(a,b) kernel pair of the event-split schedule."""
     p = ROOT / "profiles" / "traffic.json"
-    if p.exists():
-        return json.loads(p.read_text()).get(workload)
-    return None
+    if not p.exists():
+        return None
+    t = json.loads(p.read_text())
+    if schedule == "event":
+        per_event = t.get(workload + "/event_bytes_per_event")
+        return None if per_event is None else int(per_event * counters_per_rank["n_events"])
+    return t.get(workload)
 
 
 class ClockSampler:
@@ -113,6 +119,18 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+ROOFLINE_NOTE = {
+    "fused": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4) per launch of the fused kernel, "
+             "which keeps particle state in registers and the tables in L2/SMEM: real DRAM traffic is far below this "
+             "model and the kernel is fp64-issue bound, see DESIGN.md",
+    "event": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4) per step; a 'launch' is the "
+             "whole pass loop of one step (flight kernel + S(a,b) kernel per event, kernel_split has their CUDA-event "
+             "times and counts); particle state really streams through HBM here (traffic = ncu DRAM bytes). The "
+             "dominant S(a,b) kernel is bound by L1/shared-memory wavefronts of the table gathers, not by HBM: see "
+             "DESIGN.md and profiles/",
+}
 
 
 def algorithmic_bytes(c: dict) -> int:
@@ -253,6 +271,19 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, kernel_ms = t.tolist()
     launches_per_step = drv.last_launches
+    schedule = "fused" if launches_per_step == 1 else "event"
+    kernel_split = None
+    if schedule == "event":
+        # one more (untimed) step with CUDA events around every kernel: the flight / S(a,b) split of the device time
+        drv.set_options(device=local_rank, profile=1)
+        step()
+        sync_all()
+        flight_ms, tsl_ms = drv.last_kernel_ms()
+        drv.set_options(device=local_rank)
+        kernel_split = {"event_flight_kernel_ms": flight_ms, "event_tsl_kernel_ms": tsl_ms,
+                        "dominant": "event_tsl_kernel" if tsl_ms >= flight_ms else "event_flight_kernel",
+                        "dominant_share": max(flight_ms, tsl_ms) / max(flight_ms + tsl_ms, 1e-9),
+                        "launches": launches_per_step}
     c = dict(zip([n for n, _ in capi.Counters._fields_], counters.tolist()))
     assert c["n_histories"] == total_histories, (c["n_histories"], total_histories)
     assert c["n_lost"] == 0 and c["n_physics_errors"] == 0 and c["n_capacity_overflow"] == 0, c
@@ -288,11 +319,10 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
         "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": dram_traffic_per_launch(workload), "peak_source": peak_src,
+                     "traffic": dram_traffic_per_step(workload, schedule, per_rank), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": 1e3 * launch_s,
-                     "note": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4); the fused "
-                             "kernel keeps particle state in registers and the tables in L2/SMEM, so real DRAM traffic "
-                             "is far below this model: the kernel is fp64-issue bound, see DESIGN.md"},
+                     "schedule": schedule, "kernel_split": kernel_split,
+                     "note": ROOFLINE_NOTE[schedule]},
         "counters_per_step": c,
         "config": {"workload": w["name"], "histories_per_gpu_per_step": n_per_gpu, "rng": "minstd_compat (bit-exact)",
                    "estimator_bins": int(bins), "l2": "flushed between timed steps (256 MiB write, untimed)",

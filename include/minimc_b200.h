@@ -248,7 +248,7 @@ typedef struct mmc_run_options {
   uint32_t schedule;                /* mmc_schedule; 0 = library default */
   void* stream;                     /* cudaStream_t; NULL = the library's own stream */
   uint32_t event_slots;             /* MMC_SCHEDULE_EVENT: histories in flight at once (0 = library default) */
-  uint32_t reserved;
+  uint32_t profile;                 /* MMC_SCHEDULE_EVENT: 1 = time every kernel with CUDA events (mmc_world_last_kernel_ms) */
 } mmc_run_options;
 
 int mmc_abi_version(void);
@@ -267,6 +267,9 @@ uint64_t mmc_world_bytes(const mmc_world* world);
 
 /* Kernels launched by the last mmc_fixed_source_run[_device] on this world (1 for the fused schedule). */
 uint64_t mmc_world_last_launches(const mmc_world* world);
+/* With mmc_run_options.profile = 1: device time (ms, CUDA events on the run's stream) the last event-split run spent in
+ * its flight kernels and in its S(a,b) kernels. */
+void mmc_world_last_kernel_ms(const mmc_world* world, double* flight_ms, double* tsl_ms);
 
 /* Total number of bins of estimator e = cosine.n_bins * energy.n_bins
  * (ParticleBins::size, Bins.cpp:192-194). */
@@ -405,6 +408,7 @@ void mmc_driver_release_device(mmc_driver* driver);
 uint64_t mmc_driver_table_bytes(mmc_driver* driver);
 /* Kernels launched by the driver's last Solve() / run_device on this rank (mmc_world_last_launches). */
 uint64_t mmc_driver_last_launches(mmc_driver* driver);
+void mmc_driver_last_kernel_ms(mmc_driver* driver, double* flight_ms, double* tsl_ms);
 /* Parity hook: mmc_trace_histories for histories [first, first + n) of a fixed-source deck. */
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records);

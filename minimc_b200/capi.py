@@ -90,7 +90,7 @@ class RunOptions(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("tracking", C.c_int32), ("rng_mode", C.c_int32),
         ("secondary_capacity", C.c_uint32), ("pending_capacity", C.c_uint32), ("blocks_per_sm", C.c_uint32),
-        ("schedule", C.c_uint32), ("stream", C.c_void_p), ("event_slots", C.c_uint32), ("reserved", C.c_uint32),
+        ("schedule", C.c_uint32), ("stream", C.c_void_p), ("event_slots", C.c_uint32), ("profile", C.c_uint32),
     ]
 
 
@@ -109,7 +109,7 @@ EXPORTS = (
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
     "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
-    "mmc_world_last_launches", "mmc_driver_last_launches",
+    "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms",
 )
 
 _lib = None
@@ -216,6 +216,9 @@ def load() -> C.CDLL:
     for fn in (lib.mmc_world_last_launches, lib.mmc_driver_last_launches):
         fn.restype = C.c_uint64
         fn.argtypes = [C.c_void_p]
+    for fn in (lib.mmc_world_last_kernel_ms, lib.mmc_driver_last_kernel_ms):
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mmc_driver_keff.restype = C.c_int
     lib.mmc_driver_keff.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t)]
     if lib.mmc_abi_version() != ABI_VERSION:
@@ -474,7 +477,7 @@ class Driver:
         return int(load().mmc_driver_total_bins(self._handle))
 
     def set_options(self, *, device=-1, secondary_capacity=0, pending_capacity=0, blocks_per_sm=0, rng_mode=RNG_MINSTD_COMPAT,
-                    schedule=0, event_slots=0):
+                    schedule=0, event_slots=0, profile=0):
         o = RunOptions()
         o.struct_size = C.sizeof(RunOptions)
         o.device = device
@@ -484,6 +487,7 @@ class Driver:
         o.blocks_per_sm = blocks_per_sm
         o.schedule = schedule
         o.event_slots = event_slots
+        o.profile = profile
         check(load().mmc_driver_set_options(self._handle, C.byref(o)))
 
     def set_shard(self, rank: int, world_size: int):
@@ -539,6 +543,12 @@ class Driver:
     @property
     def last_launches(self) -> int:
         return int(load().mmc_driver_last_launches(self._handle))
+
+    def last_kernel_ms(self):
+        """(flight ms, S(a,b) ms) of the last event-split run made with set_options(profile=1)."""
+        a, b = C.c_double(), C.c_double()
+        load().mmc_driver_last_kernel_ms(self._handle, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def trace(self, first_history: int, n_histories: int, cap=1 << 18):
         records = (EventRecord * cap)()

@@ -92,6 +92,7 @@ struct mmc_world {
   size_t event_bytes = 0;
   unsigned int* h_event_counts = nullptr;
   uint64_t last_launches = 0;  // kernels launched by the last event-split run
+  double last_flight_ms = 0, last_tsl_ms = 0;  // profile mode: device time of the flight / S(a,b) kernels
   // k-eigenvalue scratch
   BankSite* d_unordered = nullptr;
   size_t unordered_bytes = 0;
@@ -276,6 +277,7 @@ struct Prepared {
   std::vector<double> bounds;
   LaunchConfig cfg{};
   cudaStream_t stream = nullptr;
+  bool profile = false;         // time every kernel of the event-split schedule with CUDA events
   bool event_schedule = false;  // event-split kernels (event_loop.cu) instead of the fused kernel
   uint32_t event_slots = 0;     // histories in flight at once
 };
@@ -372,6 +374,7 @@ int prepare_run(
   if (const char* env = std::getenv("MMC_EVENT_SLOTS")) {
     if (slots == 0) slots = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
   }
+  out.profile = opt.profile != 0;
   if (schedule > MMC_SCHEDULE_EVENT) return fail(MMC_ERR_INVALID, "unknown schedule %u", schedule);
   if (schedule == MMC_SCHEDULE_EVENT && (!continuous_energy || generation || trace))
     return fail(MMC_ERR_INVALID, "MMC_SCHEDULE_EVENT is for continuous-energy fixed-source runs");
@@ -437,16 +440,40 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
   MMC_CUDA(launch_event_init(b.st, b.q, p.event_slots, b.counter_replicas, p.stream));
   uint32_t alive = p.event_slots, pass = 0;
   w->last_launches = 1;
-  while (alive) {
+  // profile mode: CUDA events around every kernel of every pass (flight | S(a,b)), summed after the run
+  std::vector<cudaEvent_t> marks;
+  auto mark = [&]() -> cudaEvent_t {
+    if (!p.profile) return nullptr;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    marks.push_back(e);
+    return e;
+  };
+  int status = MMC_OK;
+  while (alive && status == MMC_OK) {
     const int batch = 8;
-    for (int k = 0; k < batch; k++, pass++)
-      MMC_CUDA(launch_event_pass(w->d_blob, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next,
-                                 d_scores, d_square, b.counter_replicas, tsl, p.stream));
+    for (int k = 0; k < batch && status == MMC_OK; k++, pass++) {
+      if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
+      const cudaError_t err = launch_event_pass(
+          w->d_blob, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
+          b.counter_replicas, tsl, p.stream, mark());
+      if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
+      if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "launch_event_pass: %s", cudaGetErrorString(err));
+    }
     w->last_launches += 2 * batch;
-    MMC_CUDA(cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream));
-    MMC_CUDA(cudaStreamSynchronize(p.stream));
+    cudaError_t err = cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(p.stream);
+    if (err != cudaSuccess && status == MMC_OK) status = fail(MMC_ERR_CUDA, "event-split pass loop: %s", cudaGetErrorString(err));
     alive = w->h_event_counts[pass & 1u];
   }
+  w->last_flight_ms = w->last_tsl_ms = 0;
+  for (size_t k = 0; k + 2 < marks.size() + 0 && status == MMC_OK; k += 3) {
+    float a = 0, c = 0;
+    if (cudaEventElapsedTime(&a, marks[k], marks[k + 1]) == cudaSuccess) w->last_flight_ms += a;
+    if (cudaEventElapsedTime(&c, marks[k + 1], marks[k + 2]) == cudaSuccess) w->last_tsl_ms += c;
+  }
+  for (cudaEvent_t e : marks) cudaEventDestroy(e);
+  if (status != MMC_OK) return status;
   MMC_CUDA(launch_event_finish(b.counter_replicas, d_counters, p.stream));
   w->last_launches += 1;
   return MMC_OK;
@@ -494,6 +521,11 @@ int mmc_device_count(void) {
 uint64_t mmc_world_bytes(const mmc_world* world) { return world ? world->blob_bytes : 0; }
 
 uint64_t mmc_world_last_launches(const mmc_world* world) { return world ? world->last_launches : 0; }
+
+void mmc_world_last_kernel_ms(const mmc_world* world, double* flight_ms, double* tsl_ms) {
+  if (flight_ms) *flight_ms = world ? world->last_flight_ms : 0;
+  if (tsl_ms) *tsl_ms = world ? world->last_tsl_ms : 0;
+}
 
 uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
   if (!e) return 0;

@@ -27,8 +27,15 @@
 #ifndef MMC_EV_FLIGHT_BLOCKS
 #define MMC_EV_FLIGHT_BLOCKS 3
 #endif
+// The S(a,b) kernel runs one persistent CTA per SM.  Measured on B200 (single_zone, hist/s): 768 threads with the
+// mode rows in shared memory 6.90e7; 512 threads with the mode rows in 40 registers per lane 7.18e7 (384: 6.64e7,
+// 640: 6.52e7).  Shared-memory rows keep the kernel at the 128 B/clk/SM shared-memory roof (ncu: 73 % of peak L1
+// wavefronts, 63 % of them shared); register rows trade a third of the warps for a third of the wavefronts.
+#ifndef MMC_EV_TSL_ROWS_IN_REGS
+#define MMC_EV_TSL_ROWS_IN_REGS 1
+#endif
 #ifndef MMC_EV_TSL_THREADS
-#define MMC_EV_TSL_THREADS 768  // one persistent CTA per SM
+#define MMC_EV_TSL_THREADS (MMC_EV_TSL_ROWS_IN_REGS ? 512 : 768)
 #endif
 
 namespace mmc {
@@ -37,7 +44,7 @@ namespace {
 
 constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
 constexpr int kTslThreads = MMC_EV_TSL_THREADS;
-constexpr size_t kTslRowBytes = 10 * kTslThreads * sizeof(double2);
+constexpr size_t kTslRowBytes = MMC_EV_TSL_ROWS_IN_REGS ? 0 : 10 * kTslThreads * sizeof(double2);
 
 // exclusive prefix of this warp among the CTA's warp totals, and the CTA total
 __device__ __forceinline__ uint32_t warp_prefix(const uint32_t* totals, uint32_t warp, uint32_t& block_total) {
@@ -277,8 +284,8 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     const char* __restrict__ world_g, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
     uint32_t pass, unsigned long long* counter_replicas) {
   extern __shared__ __align__(16) char smem[];
-  double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
-  char* s_sc = smem + 10 * kTslThreads * sizeof(double2);
+  [[maybe_unused]] double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
+  char* s_sc = smem + kTslRowBytes;
   const uint32_t parity = pass & 1u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     q.count[parity] = 0;             // the alive queue this pass consumed: the next pass appends to it
@@ -295,7 +302,11 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     __syncthreads();
   }
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if MMC_EV_TSL_ROWS_IN_REGS
+  ce::RegisterRows<kSharedSc> rows(s_sc, w.h->off_sc_arena);
+#else
   ce::SharedRows<kTslThreads, kSharedSc> rows(s_rows, s_sc, w.h->off_sc_arena);
+#endif
   for (uint32_t base = (blockIdx.x * kWarps + warp) * 32u; base < n; base += gridDim.x * kWarps * 32u) {
     const uint32_t i = base + lane;
     if (i >= n) continue;
@@ -345,7 +356,7 @@ cudaError_t launch_event_pass(
     const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
-    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream) {
+    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream, cudaEvent_t after_flight) {
   const uint32_t blocks = (alive_upper_bound + kThreadsPerBlock - 1) / kThreadsPerBlock;
   if (blocks == 0) return cudaSuccess;
   if (run.tracking == MMC_TRACK_CELL_DELTA)
@@ -356,6 +367,7 @@ cudaError_t launch_event_pass(
     event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kThreadsPerBlock, 0, stream>>>(
         world_d, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
+  if (after_flight) cudaEventRecord(after_flight, stream);
   // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queue can feed
   const uint32_t per_cta = kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;

@@ -89,7 +89,8 @@ cudaError_t launch_event_pass(
     const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
-    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream);
+    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream,
+    cudaEvent_t after_flight = nullptr);
 // shared-memory plan of the S(a,b) kernel for a world (opts the kernels into their dynamic shared memory)
 cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out);
 cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream);

@@ -181,6 +181,17 @@ uint64_t mmc_driver_last_launches(mmc_driver* driver) {
   }
 }
 
+void mmc_driver_last_kernel_ms(mmc_driver* driver, double* flight_ms, double* tsl_ms) {
+  if (flight_ms) *flight_ms = 0;
+  if (tsl_ms) *tsl_ms = 0;
+  if (!driver) return;
+  try {
+    mmc_world_last_kernel_ms(driver->driver->device_world_handle(), flight_ms, tsl_ms);
+  } catch (const std::exception& e) {
+    mmc::set_last_error(MMC_ERR_INVALID, e.what());
+  }
+}
+
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records) {
   return Guard([&] {

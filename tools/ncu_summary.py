@@ -27,6 +27,10 @@ KEYS = [
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    # the gather roofs: L1 wavefronts (one per distinct cache line / shared-memory bank pass of a load instruction)
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors.sum", "lts__t_sectors.sum", "sm__cycles_elapsed.max",
 ]
 
 
