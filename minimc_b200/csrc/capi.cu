@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <type_traits>
 #include <string>
 #include <vector>
@@ -22,7 +24,9 @@ using namespace mmc;
 
 namespace {
 
-constexpr uint32_t kDefaultEventSlots = 1u << 21;  // histories in flight in the event-split schedule (measured choice)
+// histories in flight in the event-split schedule.  Measured on B200, single_zone, 2^23 histories: 2^18 slots 4.4e7,
+// 2^20 8.06e7, 2^21 7.99e7, 2^22 7.5e7 hist/s (fewer slots: more, smaller passes; more slots: a longer drain tail)
+constexpr uint32_t kDefaultEventSlots = 1u << 20;
 
 thread_local std::string g_error;
 
@@ -69,6 +73,51 @@ int set_last_error(int status, const std::string& message) {
   return status;
 }
 }  // namespace mmc
+
+// Scratch recycling between worlds of one process: a Driver that is rebuilt for every batch (the e2e leg of bench.py
+// does exactly that) would otherwise cudaMalloc / cudaFree ~1 GB of particle state and pending tables per solve.
+// One parked buffer per (device, kind); a world takes it on its first need and parks its own on destruction.
+namespace {
+enum ScratchKind { kScratchSites = 0, kScratchPending = 1, kScratchEvent = 2, kScratchKinds = 3 };
+struct ParkedBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+std::mutex g_scratch_mutex;
+std::map<std::pair<int, int>, ParkedBuffer> g_scratch_parked;
+
+// a buffer of at least `need` bytes: the parked one if it is large enough, else a fresh allocation
+cudaError_t scratch_acquire(int device, ScratchKind kind, size_t need, void** ptr, size_t* bytes) {
+  {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    auto it = g_scratch_parked.find({device, kind});
+    if (it != g_scratch_parked.end() && it->second.bytes >= need) {
+      *ptr = it->second.ptr;
+      *bytes = it->second.bytes;
+      g_scratch_parked.erase(it);
+      return cudaSuccess;
+    }
+  }
+  const cudaError_t e = cudaMalloc(ptr, need);
+  *bytes = e == cudaSuccess ? need : 0;
+  return e;
+}
+
+void scratch_release(int device, ScratchKind kind, void* ptr, size_t bytes) {
+  if (!ptr) return;
+  void* drop = ptr;
+  {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    ParkedBuffer& slot = g_scratch_parked[{device, kind}];
+    if (bytes > slot.bytes) {
+      drop = slot.ptr;
+      slot.ptr = ptr;
+      slot.bytes = bytes;
+    }
+  }
+  if (drop) cudaFree(drop);
+}
+}  // namespace
 
 struct mmc_world {
   int device = 0;
@@ -206,19 +255,17 @@ int validate_world(const mmc_world_desc* d) {
 int ensure_scratch(mmc_world* w, size_t threads, uint32_t sec_cap, uint32_t pend_cap, size_t bounds_count) {
   const size_t need_sites = threads * sec_cap * sizeof(BankSite);
   if (need_sites > w->sites_bytes) {
-    if (w->d_sites) cudaFree(w->d_sites);
+    scratch_release(w->device, kScratchSites, w->d_sites, w->sites_bytes);
     w->d_sites = nullptr;
     w->sites_bytes = 0;
-    MMC_CUDA(cudaMalloc(&w->d_sites, need_sites));
-    w->sites_bytes = need_sites;
+    MMC_CUDA(scratch_acquire(w->device, kScratchSites, need_sites, reinterpret_cast<void**>(&w->d_sites), &w->sites_bytes));
   }
   const size_t need_pending = threads * pend_cap * sizeof(uint2);
   if (need_pending > w->pending_bytes) {
-    if (w->d_pending) cudaFree(w->d_pending);
+    scratch_release(w->device, kScratchPending, w->d_pending, w->pending_bytes);
     w->d_pending = nullptr;
     w->pending_bytes = 0;
-    MMC_CUDA(cudaMalloc(&w->d_pending, need_pending));
-    w->pending_bytes = need_pending;
+    MMC_CUDA(scratch_acquire(w->device, kScratchPending, need_pending, reinterpret_cast<void**>(&w->d_pending), &w->pending_bytes));
   }
   const size_t need_bounds = std::max<size_t>(bounds_count, 1) * sizeof(double);
   if (need_bounds > w->bounds_bytes) {
@@ -400,11 +447,10 @@ int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
   const size_t need = n * (kEventStateBytesPerSlot + 3 * sizeof(uint32_t)) + 256 +
                       kCounterReplicas * sizeof(mmc_counters);
   if (need > w->event_bytes) {
-    if (w->d_event) cudaFree(w->d_event);
+    scratch_release(w->device, kScratchEvent, w->d_event, w->event_bytes);
     w->d_event = nullptr;
     w->event_bytes = 0;
-    MMC_CUDA(cudaMalloc(&w->d_event, need));
-    w->event_bytes = need;
+    MMC_CUDA(scratch_acquire(w->device, kScratchEvent, need, reinterpret_cast<void**>(&w->d_event), &w->event_bytes));
   }
   if (!w->h_event_counts) MMC_CUDA(cudaMallocHost(&w->h_event_counts, 4 * sizeof(unsigned int)));
   char* at = w->d_event;
@@ -584,12 +630,46 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   bool has_fission = false;
   for (int n = 0; G > 0 && n < d->n_nuclides; n++) has_fission = has_fission || (d->mg_reaction_mask[n] & MMC_REACTION_FISSION);
   if (G == 0 && d->n_nuclides > 0) {
-    auto table = [&b](const mmc_table1d& t) {
+    // SearchHint of a sorted, non-negative axis (world_blob.h); 0 for short or unsorted arrays
+    auto hint = [&b](const double* x, uint64_t n) -> uint32_t {
+      if (n < 8) return 0;
+      for (uint64_t i = 0; i < n; i++)
+        if (!(x[i] >= 0) || (i && x[i] < x[i - 1]) || !std::isfinite(x[i])) return 0;
+      uint64_t first_positive = 0;
+      while (first_positive < n && x[first_positive] == 0) first_positive++;
+      if (first_positive == n) return 0;
+      auto bits = [](double v) { int64_t u; std::memcpy(&u, &v, 8); return u; };
+      uint32_t shift = 52 - 6;  // at most 64 buckets per octave, fewer until the index fits 512 buckets
+      int64_t lo = 0, hi = 0;
+      for (;; shift++) {
+        lo = bits(x[first_positive]) >> shift;
+        hi = bits(x[n - 1]) >> shift;
+        if (hi - lo + 2 <= 512 || shift == 62) break;
+      }
+      SearchHint sh{};
+      sh.first_bucket = lo - 1;
+      sh.shift = shift;
+      sh.n_buckets = static_cast<uint32_t>(hi - lo + 2);
+      // cum[k] = number of elements whose bucket (clamped like the device does) is below k
+      std::vector<uint32_t> cum(sh.n_buckets + 1, 0);
+      for (uint64_t i = 0; i < n; i++) {
+        int64_t k = (bits(x[i]) >> shift) - sh.first_bucket;
+        k = std::min<int64_t>(std::max<int64_t>(k, 0), sh.n_buckets - 1);
+        cum[k + 1]++;
+      }
+      for (uint32_t k = 0; k < sh.n_buckets; k++) cum[k + 1] += cum[k];
+      std::vector<char> image(sizeof(SearchHint) + cum.size() * sizeof(uint32_t));
+      std::memcpy(image.data(), &sh, sizeof(SearchHint));
+      std::memcpy(image.data() + sizeof(SearchHint), cum.data(), cum.size() * sizeof(uint32_t));
+      return b.add(image.data(), image.size());
+    };
+    auto table = [&b, &hint](const mmc_table1d& t) {
       Table1D out{};
       out.n = static_cast<uint32_t>(t.n);
       if (t.n) {
         out.off_x = b.add(t.x, t.n);
         out.off_y = b.add(t.y, t.n);
+        out.off_hint = hint(t.x, t.n);
       }
       return out;
     };
@@ -619,7 +699,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
       b.pad();
       h.sc_arena_bytes = static_cast<uint32_t>(b.bytes.size()) - h.off_sc_arena;
     }
-    auto partitions = [&b, &sc_offsets, &sc_next](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
+    auto partitions = [&b, &sc_offsets, &sc_next, &hint](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
       std::vector<TslPartition> out(n);
       for (int i = 0; i < n; i++) {
         const mmc_tsl_partition& q = p[i];
@@ -629,6 +709,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
         o.n_T = static_cast<uint32_t>(q.n_temperature);
         o.rank = static_cast<uint32_t>(q.rank);
         o.off_cdf = b.add(q.cdf, q.n_cdf);
+        o.off_cdf_hint = hint(q.cdf, q.n_cdf);
         o.off_T = b.add(q.temperature, q.n_temperature);
         o.off_scaled_cdf_modes = sc_offsets[sc_next++];  // in the arena, same traversal order
         o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
@@ -662,6 +743,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
           tt.n_T = static_cast<uint32_t>(t.n_temperature);
           tt.rank = static_cast<uint32_t>(t.rank);
           tt.off_E = b.add(t.energy, t.n_energy);
+          tt.off_E_hint = hint(t.energy, t.n_energy);
           tt.off_T = b.add(t.temperature, t.n_temperature);
           // S[r] * scatter_xs_E[E][r]: the first product of EvaluateInelastic (ThermalScattering.cpp:264-267)
           std::vector<double> xs_SE(t.n_energy * t.rank);
@@ -676,8 +758,10 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
           tt.off_alpha_partitions = partitions(t.alpha_partitions, t.n_alpha_partitions, betas);
           tt.n_Es = static_cast<uint32_t>(Es.size());
           tt.off_Es = b.add(Es.data(), Es.size());
+          tt.off_Es_hint = hint(Es.data(), Es.size());
           tt.n_betas = static_cast<uint32_t>(betas.size());
           tt.off_betas = b.add(betas.data(), betas.size());
+          tt.off_betas_hint = hint(betas.data(), betas.size());
           tt.beta_cutoff = t.beta_cutoff;
           tt.alpha_cutoff = t.alpha_cutoff;
           tt.awr = t.awr;
@@ -719,11 +803,11 @@ void mmc_world_destroy(mmc_world* w) {
   cudaSetDevice(w->device);
   if (w->stream) cudaStreamDestroy(w->stream);
   cudaFree(w->d_blob);
-  cudaFree(w->d_sites);
-  cudaFree(w->d_pending);
+  scratch_release(w->device, kScratchSites, w->d_sites, w->sites_bytes);
+  scratch_release(w->device, kScratchPending, w->d_pending, w->pending_bytes);
   cudaFree(w->d_bounds);
   cudaFree(w->d_next);
-  cudaFree(w->d_event);
+  scratch_release(w->device, kScratchEvent, w->d_event, w->event_bytes);
   if (w->h_event_counts) cudaFreeHost(w->h_event_counts);
   cudaFree(w->d_unordered);
   cudaFree(w->d_child_count);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   __shared__ uint32_t s_totals[3][kWarpsPerBlock];  // per-warp counts: history claims, live slots, S(a,b) slots
   __shared__ unsigned long long s_claim_base;
   __shared__ uint32_t s_queue_base[2];
-  __shared__ uint32_t s_counters[kNumCounters];
+  __shared__ uint4 s_packed[kWarpsPerBlock];  // per-warp packed counter sums
 
   const uint32_t parity = pass & 1u;
   const uint32_t first = blockIdx.x * kThreadsPerBlock;
@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   p.cell = st.cell[slot];
   p.surface = st.surface[slot];
   if (first >= n) return;  // CTA-uniform
-  if (threadIdx.x < kNumCounters) s_counters[threadIdx.x] = 0;
   const bool valid = i < n;
   const WorldView w(world_g);
   const bool has_secondaries = run.secondary_capacity > 1;
@@ -244,15 +243,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
     s_totals[1][warp] = __popc(keep_mask);
     s_totals[2][warp] = __popc(tsl_mask);
   }
-  // ---- counters: warp sums into shared memory
+  // ---- counters: the 0/1-per-lane counters packed four to a word, one warp reduction per word, no atomics
   {
-    const uint32_t v[kNumCounters] = {c.histories, c.births,      c.events, c.collisions, c.crossings, c.virtuals,
-                                      c.scores,    c.secondaries, c.banked, c.lost,       c.capacity,  c.physics};
-#pragma unroll
-    for (int k = 0; k < kNumCounters; k++) {
-      const uint32_t sum = __reduce_add_sync(kFull, v[k]);
-      if (lane == 0 && sum) atomicAdd(&s_counters[k], sum);
-    }
+    const uint32_t a = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
+    const uint32_t b = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
+    const uint32_t d = c.scores | (c.capacity << 16);  // at most kMaxEstimators + 1 each per lane
+    const uint32_t sa = __reduce_add_sync(kFull, a), sb = __reduce_add_sync(kFull, b), sd = __reduce_add_sync(kFull, d);
+    const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
+    if (lane == 0) s_packed[warp] = make_uint4(sa, sb, sd, ss);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -261,9 +259,23 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
     s_queue_base[0] = keep_total ? atomicAdd(&q.count[parity ^ 1u], keep_total) : 0u;
     s_queue_base[1] = tsl_total ? atomicAdd(&q.count[2u + parity], tsl_total) : 0u;
   }
-  if (threadIdx.x < kNumCounters && s_counters[threadIdx.x])
-    atomicAdd(counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters + threadIdx.x,
-              static_cast<unsigned long long>(s_counters[threadIdx.x]));
+  if (threadIdx.x < kNumCounters) {
+    // mmc_counters order: histories, births, events, collisions, crossings, virtual, scores, secondaries, banked,
+    // lost, capacity, physics -> (word, shift, mask) of the packed sums
+    const uint32_t k = threadIdx.x;
+    const uint32_t word = (k == 2 || k == 3 || k == 4 || k == 5) ? 0u : (k == 0 || k == 1 || k == 9 || k == 11) ? 1u : (k == 6 || k == 10) ? 2u : 3u;
+    const uint32_t shift = k == 3 ? 8u : k == 4 ? 16u : k == 5 ? 24u : k == 1 ? 8u : k == 9 ? 16u : k == 11 ? 24u : k == 10 ? 16u : 0u;
+    const uint32_t mask = word < 2u ? 0xffu : word == 2u ? 0xffffu : 0xffffffffu;
+    uint32_t sum = 0;
+    if (k != 8) {
+      for (int wi = 0; wi < kWarpsPerBlock; wi++) {
+        const uint4 v = s_packed[wi];
+        const uint32_t field = word == 0u ? v.x : word == 1u ? v.y : word == 2u ? v.z : v.w;
+        sum += (field >> shift) & mask;
+      }
+    }
+    if (sum) atomicAdd(counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters + k, static_cast<unsigned long long>(sum));
+  }
   __syncthreads();
   uint32_t total;
   if (keep) q.alive[parity ^ 1u][s_queue_base[0] + warp_prefix(s_totals[1], warp, total) + __popc(keep_mask & lanes_below)] = slot;

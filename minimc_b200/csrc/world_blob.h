@@ -70,7 +70,19 @@ constexpr int kMaxCeReactions = 4;  // per nuclide: capture, scatter, fission (+
 struct Table1D {
   uint32_t n;
   uint32_t off_x, off_y;  // double[n] each
-  uint32_t pad;
+  uint32_t off_hint;      // SearchHint of x, 0 = none
+};
+
+// Bucket index over a sorted, non-negative array x[n] that narrows std::upper_bound to a few elements: the bucket
+// of a value is its IEEE-754 bit pattern shifted right (exponent + leading mantissa bits: monotone in the value, a
+// piecewise-linear log2), cum[k] = number of elements in buckets below k.  upper_bound(v) lies in
+// [cum[k(v)], cum[k(v)+1]]; searching that range gives the same index as searching the whole array because the array
+// is sorted (checked when the world is built; arrays that are not sorted get no hint and the plain search).
+struct SearchHint {
+  int64_t first_bucket;  // bucket number (bits >> shift) of the first positive element, minus 1
+  uint32_t shift;
+  uint32_t n_buckets;    // cum has n_buckets + 1 entries; bucket 0 = everything below the first positive element
+  // uint32_t cum[n_buckets + 1] follows
 };
 
 // ThermalScattering::BetaPartition / AlphaPartition
@@ -79,7 +91,7 @@ struct TslPartition {
   uint32_t off_cdf;        // double[n_cdf]
   uint32_t off_T;          // double[n_T]
   uint32_t off_scaled_cdf_modes;  // double[n_cdf][rank]: S[r] * CDF_modes[cdf][r] (the reference's first product)
-  uint32_t pad0;
+  uint32_t off_cdf_hint;   // SearchHint of cdf, 0 = none
   uint32_t off_modes;      // double[n_grid][n_T][rank]
   uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
   uint32_t pad[2];
@@ -88,13 +100,13 @@ struct TslPartition {
 // ThermalScattering
 struct TslTable {
   Table1D majorant;
-  uint32_t n_E, n_T, rank, pad0;
-  uint32_t off_E, off_T, off_xs_SE, pad2, off_xs_T;  // off_xs_SE: double[n_E][rank] = S[r] * scatter_xs_E[E][r]
+  uint32_t n_E, n_T, rank, off_E_hint;
+  uint32_t off_E, off_T, off_xs_SE, off_Es_hint, off_xs_T;  // off_xs_SE: double[n_E][rank] = S[r] * scatter_xs_E[E][r]
   uint32_t n_beta_partitions, n_alpha_partitions;
   uint32_t off_beta_partitions, off_alpha_partitions;  // TslPartition[]
   uint32_t n_Es, off_Es;        // concatenated incident energies of the beta partitions (ThermalScattering::Es)
   uint32_t n_betas, off_betas;  // concatenated betas of the alpha partitions (ThermalScattering::betas)
-  uint32_t pad1;
+  uint32_t off_betas_hint;      // SearchHints of E / Es / betas: off_E_hint, off_Es_hint, off_betas_hint
   double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
 };
 
