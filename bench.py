@@ -18,9 +18,9 @@ Workloads (config.workload) -- BASELINE.json `configs`:
 A step = one pass of the hot path over --histories-per-gpu histories per GPU (weak scaling): rank r transports
 histories [r*n, (r+1)*n) of the N*n total, then the integer tallies and counters are all-reduced (NCCL).
 `value`  : device-timed (CUDA events on the launch stream), tables resident in HBM.
-`e2e`    : the same step through the reference-facing call with HOST buffers: Driver::Solve() of the C++ host after
-           dropping its device tables -- flatten -> mmc_world_create (H2D of the tables) -> mmc_fixed_source_run (H2D
-           of the bin boundaries, D2H of tallies + counters).
+`e2e`    : the same step through the reference-facing call with HOST buffers: the C++ host flattens its World again
+           and uploads the tables from pinned host memory (mmc_world_update), then Driver::Solve() ->
+           mmc_fixed_source_run (H2D of the bin boundaries, D2H of tallies + counters into a pinned mirror).
 `--impl reference` times the reference's own C++ (oracle/_ref/ref_harness = /root/reference/src behind shims) on the
 host cores on a bounded sample of the same deck; without a prebuilt oracle/_ref it says so.
 """
@@ -294,13 +294,15 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
     drv.set_shard(rank, world_size)
     h2d = drv.table_bytes + 8 * bins  # tables + (upper bound of) the bin-boundary array
     d2h = 2 * 8 * bins + 8 * n_counters
-    for _ in range(2):  # untimed warm-up of the host-buffer path (first-use costs of the allocator and the driver)
-        drv.release_device()
+    # every step: the World is flattened again and its tables uploaded from pinned host memory (refresh_device ->
+    # mmc_world_update), Driver::Solve() runs with HOST tally buffers (device -> host read of the result inside)
+    for _ in range(2):  # untimed warm-up of the host-buffer path
+        drv.refresh_device()
         drv.solve()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        drv.release_device()
+        drv.refresh_device()
         drv.solve()
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -348,6 +350,11 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
 
 
 def run_gpu_arm(args):
+    # NCCL and the CUDA runtime may print banners on the C-level stdout; the contract is ONE JSON line there.
+    # Everything but the final line goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -389,7 +396,8 @@ def run_gpu_arm(args):
                                   "steps": 3, "ms_per_step": extra["ms_per_step"], "e2e": extra["e2e"],
                                   "roofline_frac": extra["roofline"]["frac"],
                                   "histories_per_gpu_per_step": extra["config"]["histories_per_gpu_per_step"]}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world_size > 1:
         dist.destroy_process_group()
 

@@ -233,8 +233,12 @@ typedef struct mmc_world mmc_world; /* opaque: owns the device copy of the table
  * FUSED: one persistent kernel, a particle stays in registers from birth to death (multigroup worlds always).
  * EVENT: event-split -- particle state in HBM, one flight kernel + one S(a,b) kernel per event, live particles
  *        stream-compacted in between (continuous-energy worlds; the default for them).  The device variant of the
- *        call then synchronises the stream every few passes to read the number of live histories. */
-typedef enum mmc_schedule { MMC_SCHEDULE_AUTO = 0, MMC_SCHEDULE_FUSED = 1, MMC_SCHEDULE_EVENT = 2 } mmc_schedule;
+ *        call then synchronises the stream every few passes to read the number of live histories.
+ * EVENT_ONLY: as EVENT, without the hand-over of the last few thousand live histories to the fused kernel that EVENT
+ *        makes once every history has started (a pass over few particles costs its launch latency, not its work). */
+typedef enum mmc_schedule {
+  MMC_SCHEDULE_AUTO = 0, MMC_SCHEDULE_FUSED = 1, MMC_SCHEDULE_EVENT = 2, MMC_SCHEDULE_EVENT_ONLY = 3
+} mmc_schedule;
 
 /* Optional knobs; zero-initialise for defaults. */
 typedef struct mmc_run_options {
@@ -261,6 +265,9 @@ int mmc_device_count(void);
  * the one-off flattening of `const World`, World.cpp:20-24). */
 int mmc_world_create(const mmc_world_desc* desc, int device, mmc_world** out);
 void mmc_world_destroy(mmc_world* world);
+/* Uploads new table VALUES into an existing world (same shapes: the device image must have the same size), through
+ * the world's pinned staging buffer; no allocation.  For callers that refresh cross sections between batches. */
+int mmc_world_update(mmc_world* world, const mmc_world_desc* desc);
 
 /* Bytes of flattened tables resident on the device for this world (what mmc_world_create copied host -> device). */
 uint64_t mmc_world_bytes(const mmc_world* world);
@@ -405,6 +412,9 @@ int mmc_driver_run_device(mmc_driver* driver, uint64_t first_history, uint64_t n
                           uint64_t* d_square_scores, mmc_counters* d_counters, void* stream);
 /* Drops the device copy of the World, so that the next Solve() uploads the tables again; and its size in bytes. */
 void mmc_driver_release_device(mmc_driver* driver);
+/* Flattens the driver's World again and uploads it into the existing device world (mmc_world_update); creates the
+ * device world when there is none. */
+int mmc_driver_refresh_device(mmc_driver* driver);
 uint64_t mmc_driver_table_bytes(mmc_driver* driver);
 /* Kernels launched by the driver's last Solve() / run_device on this rank (mmc_world_last_launches). */
 uint64_t mmc_driver_last_launches(mmc_driver* driver);

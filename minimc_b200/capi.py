@@ -94,7 +94,7 @@ class RunOptions(C.Structure):
     ]
 
 
-SCHEDULE_AUTO, SCHEDULE_FUSED, SCHEDULE_EVENT = 0, 1, 2  # mmc_schedule
+SCHEDULE_AUTO, SCHEDULE_FUSED, SCHEDULE_EVENT, SCHEDULE_EVENT_ONLY = 0, 1, 2, 3  # mmc_schedule
 
 
 # every symbol include/minimc_b200.h declares
@@ -109,7 +109,7 @@ EXPORTS = (
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
     "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
-    "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms",
+    "mmc_world_update", "mmc_driver_refresh_device", "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms",
 )
 
 _lib = None
@@ -213,6 +213,10 @@ def load() -> C.CDLL:
     lib.mmc_driver_table_bytes.argtypes = [C.c_void_p]
     lib.mmc_world_bytes.restype = C.c_uint64
     lib.mmc_world_bytes.argtypes = [C.c_void_p]
+    lib.mmc_driver_refresh_device.restype = C.c_int
+    lib.mmc_driver_refresh_device.argtypes = [C.c_void_p]
+    lib.mmc_world_update.restype = C.c_int
+    lib.mmc_world_update.argtypes = [C.c_void_p, C.c_void_p]
     for fn in (lib.mmc_world_last_launches, lib.mmc_driver_last_launches):
         fn.restype = C.c_uint64
         fn.argtypes = [C.c_void_p]
@@ -535,6 +539,10 @@ class Driver:
 
     def release_device(self):
         load().mmc_driver_release_device(self._handle)
+
+    def refresh_device(self):
+        """Flattens the World again and uploads the tables into the existing device world (no allocation)."""
+        check(load().mmc_driver_refresh_device(self._handle))
 
     @property
     def table_bytes(self) -> int:

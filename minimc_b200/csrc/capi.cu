@@ -27,6 +27,8 @@ namespace {
 // histories in flight in the event-split schedule.  Measured on B200, single_zone, 2^23 histories: 2^18 slots 4.4e7,
 // 2^20 8.06e7, 2^21 7.99e7, 2^22 7.5e7 hist/s (fewer slots: more, smaller passes; more slots: a longer drain tail)
 constexpr uint32_t kDefaultEventSlots = 1u << 20;
+// live histories at or below which the drain of an event-split run is handed to the fused kernel
+constexpr uint32_t kDefaultEventHandover = 1u << 15;
 
 thread_local std::string g_error;
 
@@ -122,6 +124,11 @@ void scratch_release(int device, ScratchKind kind, void* ptr, size_t bytes) {
 struct mmc_world {
   int device = 0;
   char* d_blob = nullptr;
+  char* h_blob = nullptr;  // pinned host copy of the image: the source of every upload
+  // device tally / counter buffers and their pinned host mirror, reused by mmc_fixed_source_run
+  unsigned long long* d_tally = nullptr;
+  unsigned long long* h_tally = nullptr;
+  size_t tally_words = 0;
   uint32_t blob_bytes = 0;
   WorldHeader header{};
   bool has_fission = false;
@@ -327,6 +334,7 @@ struct Prepared {
   bool profile = false;         // time every kernel of the event-split schedule with CUDA events
   bool event_schedule = false;  // event-split kernels (event_loop.cu) instead of the fused kernel
   uint32_t event_slots = 0;     // histories in flight at once
+  uint32_t event_handover = 0;  // live histories at or below which the drain goes to the fused kernel (0: never)
 };
 
 int prepare_run(
@@ -422,8 +430,8 @@ int prepare_run(
     if (slots == 0) slots = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
   }
   out.profile = opt.profile != 0;
-  if (schedule > MMC_SCHEDULE_EVENT) return fail(MMC_ERR_INVALID, "unknown schedule %u", schedule);
-  if (schedule == MMC_SCHEDULE_EVENT && (!continuous_energy || generation || trace))
+  if (schedule > MMC_SCHEDULE_EVENT_ONLY) return fail(MMC_ERR_INVALID, "unknown schedule %u", schedule);
+  if (schedule >= MMC_SCHEDULE_EVENT && (!continuous_energy || generation || trace))
     return fail(MMC_ERR_INVALID, "MMC_SCHEDULE_EVENT is for continuous-energy fixed-source runs");
   out.event_schedule = continuous_energy && !generation && !trace && schedule != MMC_SCHEDULE_FUSED;
   if (out.event_schedule) {
@@ -431,6 +439,10 @@ int prepare_run(
     // worlds with fission keep a secondary deque per slot: bound its memory
     if (w->has_fission) slots = std::min<uint32_t>(slots, 1u << 18);
     out.event_slots = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(n_histories, 1), slots));
+    out.event_handover = schedule == MMC_SCHEDULE_EVENT_ONLY ? 0u : kDefaultEventHandover;
+    if (const char* env = std::getenv("MMC_EVENT_HANDOVER")) {
+      if (schedule != MMC_SCHEDULE_EVENT_ONLY) out.event_handover = static_cast<uint32_t>(std::strtoul(env, nullptr, 10));
+    }
   }
   return MMC_OK;
 }
@@ -452,7 +464,7 @@ int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
     w->event_bytes = 0;
     MMC_CUDA(scratch_acquire(w->device, kScratchEvent, need, reinterpret_cast<void**>(&w->d_event), &w->event_bytes));
   }
-  if (!w->h_event_counts) MMC_CUDA(cudaMallocHost(&w->h_event_counts, 4 * sizeof(unsigned int)));
+  if (!w->h_event_counts) MMC_CUDA(cudaMallocHost(&w->h_event_counts, 8 * sizeof(unsigned int)));
   char* at = w->d_event;
   auto take = [&](auto*& ptr, size_t bytes) {
     ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(at);
@@ -508,9 +520,30 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     }
     w->last_launches += 2 * batch;
     cudaError_t err = cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(w->h_event_counts + 4, w->d_next, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p.stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(p.stream);
     if (err != cudaSuccess && status == MMC_OK) status = fail(MMC_ERR_CUDA, "event-split pass loop: %s", cudaGetErrorString(err));
     alive = w->h_event_counts[pass & 1u];
+    unsigned long long claimed = 0;
+    std::memcpy(&claimed, w->h_event_counts + 4, sizeof(claimed));
+    if (status == MMC_OK && alive && alive <= p.event_handover && claimed >= p.run.n_histories) {
+      // The drain: every history has started and few are still alive.  A pass now costs its two launches' latency,
+      // not their work, so the survivors are handed to the fused kernel, one thread per slot, and run to their end.
+      ResumeIO resume;
+      resume.slots = b.q.alive[pass & 1u];
+      resume.n = b.q.count + (pass & 1u);
+      resume.st = b.st;
+      LaunchConfig cfg;
+      cfg.blocks = static_cast<int>((alive + kThreadsPerBlock - 1) / kThreadsPerBlock);
+      RunSpec run = p.run;
+      run.chunk = 32;
+      err = launch_fixed_source(cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
+                                d_counters, nullptr, p.stream, &resume);
+      if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "hand-over to the fused kernel: %s", cudaGetErrorString(err));
+      w->last_launches += 1;
+      alive = 0;
+    }
   }
   w->last_flight_ms = w->last_tsl_ms = 0;
   for (size_t k = 0; k + 2 < marks.size() + 0 && status == MMC_OK; k += 3) {
@@ -579,19 +612,12 @@ uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
   return n(e->cosine) * n(e->energy);
 }
 
-int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
-  if (!out) return fail(MMC_ERR_INVALID, "out is NULL");
-  *out = nullptr;
-  if (int s = validate_world(d)) return s;
-  if (mmc_device_count() < 1)
-    return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible: minimc_b200 has no CPU transport path");
-  if (device < 0) MMC_CUDA(cudaGetDevice(&device));
-  MMC_CUDA(cudaSetDevice(device));
-
+namespace {
+// Flattens a validated world description into the device image (world_blob.h).
+int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& header_out, bool& has_fission_out) {
   const int G = d->n_groups;
   const int nnz_cell = d->cell_surface_begin[d->n_cells];
   const int nnz_mat = d->n_materials ? d->material_nuclide_begin[d->n_materials] : 0;
-  BlobBuilder b;
   std::vector<int32_t> packed(nnz_cell);
   for (int k = 0; k < nnz_cell; k++) packed[k] = (d->cell_surface_index[k] << 1) | (d->cell_surface_sense[k] ? 1 : 0);
   std::vector<int32_t> field_kind(d->n_cells, MMC_FIELD_CONSTANT);
@@ -776,6 +802,24 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   if (b.bytes.size() > 0xfffffff0ull) return fail(MMC_ERR_INVALID, "world tables exceed 4 GiB");
   h.total_bytes = static_cast<uint32_t>(b.bytes.size());
   b.header() = h;
+  header_out = h;
+  has_fission_out = has_fission;
+  return MMC_OK;
+}
+}  // namespace
+
+int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
+  if (!out) return fail(MMC_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int s = validate_world(d)) return s;
+  if (mmc_device_count() < 1)
+    return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible: minimc_b200 has no CPU transport path");
+  if (device < 0) MMC_CUDA(cudaGetDevice(&device));
+  MMC_CUDA(cudaSetDevice(device));
+  BlobBuilder b;
+  WorldHeader h{};
+  bool has_fission = false;
+  if (int s = build_world_blob(d, b, h, has_fission)) return s;
 
   auto* w = new mmc_world;
   w->device = device;
@@ -785,7 +829,9 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   cudaDeviceProp prop{};
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) e = cudaMalloc(&w->d_blob, w->blob_bytes);
-  if (e == cudaSuccess) e = cudaMemcpy(w->d_blob, b.bytes.data(), w->blob_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMallocHost(&w->h_blob, w->blob_bytes);  // pinned staging copy of the image
+  if (e == cudaSuccess) std::memcpy(w->h_blob, b.bytes.data(), w->blob_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(w->d_blob, w->h_blob, w->blob_bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&w->d_next, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -798,11 +844,32 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   return MMC_OK;
 }
 
+int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  if (int s = validate_world(d)) return s;
+  BlobBuilder b;
+  WorldHeader h{};
+  bool has_fission = false;
+  if (int s = build_world_blob(d, b, h, has_fission)) return s;
+  if (h.total_bytes != w->blob_bytes || has_fission != w->has_fission || h.n_groups != w->header.n_groups)
+    return fail(MMC_ERR_INVALID, "mmc_world_update: the new tables have a different shape (%u bytes, world holds %u): "
+                "create a new world", h.total_bytes, w->blob_bytes);
+  MMC_CUDA(cudaSetDevice(w->device));
+  std::memcpy(w->h_blob, b.bytes.data(), w->blob_bytes);
+  MMC_CUDA(cudaMemcpyAsync(w->d_blob, w->h_blob, w->blob_bytes, cudaMemcpyHostToDevice, w->stream));
+  MMC_CUDA(cudaStreamSynchronize(w->stream));
+  w->header = h;
+  return MMC_OK;
+}
+
 void mmc_world_destroy(mmc_world* w) {
   if (!w) return;
   cudaSetDevice(w->device);
   if (w->stream) cudaStreamDestroy(w->stream);
   cudaFree(w->d_blob);
+  if (w->h_blob) cudaFreeHost(w->h_blob);
+  cudaFree(w->d_tally);
+  if (w->h_tally) cudaFreeHost(w->h_tally);
   scratch_release(w->device, kScratchSites, w->d_sites, w->sites_bytes);
   scratch_release(w->device, kScratchPending, w->d_pending, w->pending_bytes);
   cudaFree(w->d_bounds);
@@ -950,30 +1017,31 @@ int mmc_fixed_source_run(
   if (options) opt = *options;
   opt.struct_size = sizeof(mmc_run_options);
   cudaStream_t stream = opt.stream ? static_cast<cudaStream_t>(opt.stream) : world->stream;
-  unsigned long long* d_tally = nullptr;
-  mmc_counters* d_counters = nullptr;
-  const size_t tally_bytes = std::max<uint64_t>(total_bins, 1) * 2 * sizeof(unsigned long long);
-  MMC_CUDA(cudaMalloc(&d_tally, tally_bytes));
-  cudaError_t e = cudaMalloc(&d_counters, sizeof(mmc_counters));
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_tally, 0, tally_bytes, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_counters, 0, sizeof(mmc_counters), stream);
-  int status = MMC_OK;
-  if (e != cudaSuccess) status = fail(MMC_ERR_CUDA, "mmc_fixed_source_run: %s", cudaGetErrorString(e));
-  if (status == MMC_OK)
-    status = mmc_fixed_source_run_device(
-        world, source, estimators, n_estimators, seed0, first_history, n_histories, &opt,
-        reinterpret_cast<uint64_t*>(d_tally), reinterpret_cast<uint64_t*>(d_tally + total_bins), d_counters);
-  std::vector<unsigned long long> h_tally(std::max<uint64_t>(total_bins, 1) * 2);
-  mmc_counters h_counters{};
-  if (status == MMC_OK) {
-    e = cudaMemcpyAsync(h_tally.data(), d_tally, tally_bytes, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_counters, d_counters, sizeof(mmc_counters), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) status = fail(MMC_ERR_CUDA, "mmc_fixed_source_run: %s", cudaGetErrorString(e));
+  // [scores | square_scores | counters] in one device buffer with a pinned host mirror, both kept by the world
+  auto* w = const_cast<mmc_world*>(world);
+  constexpr size_t kCounterWords = sizeof(mmc_counters) / sizeof(unsigned long long);
+  const size_t words = 2 * total_bins + kCounterWords;
+  if (words > w->tally_words) {
+    cudaFree(w->d_tally);
+    if (w->h_tally) cudaFreeHost(w->h_tally);
+    w->d_tally = w->h_tally = nullptr;
+    w->tally_words = 0;
+    MMC_CUDA(cudaMalloc(&w->d_tally, words * sizeof(unsigned long long)));
+    MMC_CUDA(cudaMallocHost(&w->h_tally, words * sizeof(unsigned long long)));
+    w->tally_words = words;
   }
-  cudaFree(d_tally);
-  cudaFree(d_counters);
+  unsigned long long* d_tally = w->d_tally;
+  mmc_counters* d_counters = reinterpret_cast<mmc_counters*>(d_tally + 2 * total_bins);
+  MMC_CUDA(cudaMemsetAsync(d_tally, 0, words * sizeof(unsigned long long), stream));
+  int status = mmc_fixed_source_run_device(
+      world, source, estimators, n_estimators, seed0, first_history, n_histories, &opt,
+      reinterpret_cast<uint64_t*>(d_tally), reinterpret_cast<uint64_t*>(d_tally + total_bins), d_counters);
   if (status != MMC_OK) return status;
+  MMC_CUDA(cudaMemcpyAsync(w->h_tally, d_tally, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  MMC_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long* h_tally = w->h_tally;
+  mmc_counters h_counters{};
+  std::memcpy(&h_counters, h_tally + 2 * total_bins, sizeof(mmc_counters));
   // Scorable::operator+= (Scorable.cpp:37-48): integer-valued, exact below 2^53
   for (uint64_t i = 0; i < total_bins; i++) {
     scores[i] += static_cast<double>(h_tally[i]);

@@ -75,7 +75,7 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
   if (i < kCounterReplicas * kNumCounters) counter_replicas[i] = 0;
   if (i == 0) {
     q.count[0] = n_slots;
-    q.count[1] = q.count[2] = q.count[3] = 0;
+    q.count[1] = q.count[2] = q.count[3] = q.count[4] = 0;
   }
 }
 
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   p.rng.x = st.rng[slot];
   p.cell = st.cell[slot];
   p.surface = st.surface[slot];
+  if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = 0;  // chunk counter of this pass's S(a,b) kernel
   if (first >= n) return;  // CTA-uniform
   const bool valid = i < n;
   const WorldView w(world_g);
@@ -313,15 +314,21 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     for (uint32_t k = threadIdx.x; k < w.h->sc_arena_bytes / 16; k += kTslThreads) dst[k] = __ldg(src + k);
     __syncthreads();
   }
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
 #if MMC_EV_TSL_ROWS_IN_REGS
   ce::RegisterRows<kSharedSc> rows(s_sc, w.h->off_sc_arena);
 #else
   ce::SharedRows<kTslThreads, kSharedSc> rows(s_rows, s_sc, w.h->off_sc_arena);
 #endif
-  for (uint32_t base = (blockIdx.x * kWarps + warp) * 32u; base < n; base += gridDim.x * kWarps * 32u) {
+  // warps claim chunks of 32 queue entries from one counter: a scatter takes 20-60 reconstructions, so a static
+  // split leaves the unlucky warps running alone at the end of every pass
+  while (true) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&q.count[4], 32u);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n) break;
     const uint32_t i = base + lane;
-    if (i >= n) continue;
+    if (i < n) {  // no early `continue`: every lane must come back to the shuffle above
     const uint32_t slot = q.tsl[i];
     Particle p;
     p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
       unsigned long long* mine = counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters;
       atomicAdd(mine + 3, ~0ull);  // n_collisions - 1
       atomicAdd(mine + 11, 1ull);  // n_physics_errors + 1
+    }
     }
   }
 }

@@ -67,23 +67,43 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
     unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters,
-    const __grid_constant__ GenerationIO bank) {
+    const __grid_constant__ GenerationIO bank, const __grid_constant__ ResumeIO resume) {
   extern __shared__ __align__(16) char smem[];
   const WorldView w(stage_world(world_g, run.world_bytes, run.world_in_smem != 0, smem));
 
   const uint32_t lane = threadIdx.x & 31;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // resume (ResumeIO): this thread continues slot resume.slots[tid] of the event-split schedule
+  const bool resuming = !kGeneration && resume.n != nullptr;
+  const bool adopt = resuming && tid < *resume.n;
+  const size_t scratch = adopt ? resume.slots[tid] : tid;
   SiteDeque dq;
-  dq.slots = site_scratch + tid * run.secondary_capacity;
+  dq.slots = site_scratch + scratch * run.secondary_capacity;
   dq.mask = run.secondary_capacity - 1;
   dq.head = 0;
   dq.count = 0;
-  uint2* pending = pending_scratch + tid * run.pending_capacity;
+  uint2* pending = pending_scratch + scratch * run.pending_capacity;
   uint32_t n_pending = 0;
 
   Particle p;
   p.event = MMC_EV_CAPTURE;  // "dead": forces a refill
-  bool done = false;         // no more work for this lane
+  bool done = resuming && !adopt;  // no more work for this lane (a resumed run has no scratch for extra threads)
+  if (adopt) {
+    const EventState& st = resume.st;
+    p.event = st.event[scratch];
+    p.px = st.px[scratch], p.py = st.py[scratch], p.pz = st.pz[scratch];
+    p.dx = st.dx[scratch], p.dy = st.dy[scratch], p.dz = st.dz[scratch];
+    p.energy = st.energy[scratch];
+    p.group = 0;
+    p.rng.x = st.rng[scratch];
+    p.cell = st.cell[scratch];
+    p.surface = st.surface[scratch];
+    if (run.n_estimators) n_pending = st.n_pending[scratch];
+    if (run.secondary_capacity > 1) {
+      dq.head = st.dq_head[scratch];
+      dq.count = st.dq_count[scratch];
+    }
+  }
   uint64_t w_next = 0, w_end = 0;  // warp-uniform chunk of history indices
   uint64_t history = 0;            // index of this lane's current history
   // isotropic direction owed to this lane: bit 0 = its multigroup scatter of the previous iteration, bit 1 = it
@@ -549,16 +569,18 @@ template <typename F> auto dispatch_history_kernel(int tracking, bool ce, bool g
 cudaError_t launch_fixed_source(
     const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
     uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
-    unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream) {
+    unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream,
+    const ResumeIO* resume) {
   const size_t smem = run.world_in_smem ? run.world_bytes : 0;
   const GenerationIO io = generation ? *generation : GenerationIO{};
+  const ResumeIO rs = resume ? *resume : ResumeIO{};
   return dispatch_history_kernel(run.tracking, run.continuous_energy != 0, generation != nullptr, [&](auto kernel) -> cudaError_t {
     if (smem > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
     kernel<<<cfg.blocks, kThreadsPerBlock, smem, stream>>>(
-        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io);
+        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io, rs);
     return cudaGetLastError();
   });
 }

@@ -25,12 +25,6 @@ struct GenerationIO {
   unsigned long long* child_start = nullptr; // [n_histories] where that particle's run starts in `out`
 };
 
-// generation == nullptr: fixed source; otherwise one k-eigenvalue generation over generation->in
-cudaError_t launch_fixed_source(
-    const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
-    uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
-    unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream);
-
 cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream);
 uint32_t bank_scan_blocks(uint64_t n_parents);
 cudaError_t launch_order_bank(
@@ -65,10 +59,19 @@ struct EventState {
 };
 constexpr size_t kEventStateBytesPerSlot = 8 * 8 + 8 * 4;
 
+// Hand-over from the event-split schedule to the fused kernel (the tail of a run, when too few histories are alive
+// to fill the GPU and every pass costs its launch latency): thread t < n adopts slot slots[t] -- its particle, pending
+// table and secondary deque -- and runs it, and any history it can still claim, to the end.
+struct ResumeIO {
+  const uint32_t* slots = nullptr;  // compacted live slots
+  const unsigned int* n = nullptr;  // how many (device-side count)
+  EventState st{};
+};
+
 struct EventQueues {
   uint32_t* alive[2];   // compacted slot indices, ping-pong between passes
   uint32_t* tsl;        // slots whose collision awaits S(a,b) sampling in this pass
-  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity)
+  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity), [4] chunk counter of the S(a,b) kernel
 };
 
 constexpr int kCounterReplicas = 64;
@@ -94,6 +97,13 @@ cudaError_t launch_event_pass(
 // shared-memory plan of the S(a,b) kernel for a world (opts the kernels into their dynamic shared memory)
 cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out);
 cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream);
+
+// generation == nullptr: fixed source; otherwise one k-eigenvalue generation over generation->in
+cudaError_t launch_fixed_source(
+    const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
+    uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
+    unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream,
+    const ResumeIO* resume = nullptr);
 
 // occupancy query for the fused kernel
 int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem);

@@ -108,6 +108,15 @@ std::shared_ptr<DeviceWorld> Driver::device_world() {
 
 const mmc_world* Driver::device_world_handle() { return device_world()->handle; }
 
+void Driver::RefreshDevice() {
+  if (!device_world_) {
+    device_world();
+    return;
+  }
+  device_world_->flat = FlatWorld{world};
+  if (const int status = mmc_world_update(device_world_->handle, &device_world_->flat.desc())) ThrowLastError("mmc_world_update", status);
+}
+
 // ---------------------------------------------------------------- FixedSource
 FixedSource::FixedSource(const xml::Node& root) : Driver{root}, source{ProblemNode(root, "fixedsource")} {}
 

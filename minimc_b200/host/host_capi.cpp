@@ -161,6 +161,14 @@ void mmc_driver_release_device(mmc_driver* driver) {
   if (driver) driver->driver->ReleaseDevice();
 }
 
+int mmc_driver_refresh_device(mmc_driver* driver) {
+  if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
+  return Guard([&] {
+    driver->driver->RefreshDevice();
+    return static_cast<int>(MMC_OK);
+  });
+}
+
 uint64_t mmc_driver_table_bytes(mmc_driver* driver) {
   if (!driver) return 0;
   try {

@@ -278,6 +278,8 @@ public:
   mmc_counters counters{};
   // Drops the device copy of the World (the next Solve() uploads it again); bytes it holds.
   void ReleaseDevice() { device_world_.reset(); }
+  // Flattens the World again and uploads it into the existing device world (no allocation).
+  void RefreshDevice();
   uint64_t DeviceTableBytes() { return mmc_world_bytes(device_world_handle()); }
 
   const mmc_world* device_world_handle();

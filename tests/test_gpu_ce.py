@@ -56,10 +56,12 @@ def test_ce_event_traces_match_reference_golden(tables, name, tag):
     _compare_traces(mine, ref, (name, tag) in util.CE_EXACT)
 
 
-# (schedule, event_slots): the library default (event-split for continuous energy), the fused persistent kernel, and
-# the event-split kernels with a slot count that is neither a multiple of the warp nor of the CTA, so that slots are
-# refilled many times and the compacted queues end in ragged warps
-SCHEDULES = {"default": (capi.SCHEDULE_AUTO, 0), "fused": (capi.SCHEDULE_FUSED, 0), "event_ragged": (capi.SCHEDULE_EVENT, 301)}
+# (schedule, event_slots): the library default (event-split for continuous energy, the drain handed to the fused
+# kernel), the fused persistent kernel alone, the event-split kernels to the last history with a slot count that is
+# neither a multiple of the warp nor of the CTA (slots are refilled many times, the compacted queues end in ragged
+# warps), and the hand-over from ragged queues
+SCHEDULES = {"default": (capi.SCHEDULE_AUTO, 0), "fused": (capi.SCHEDULE_FUSED, 0),
+             "event_ragged": (capi.SCHEDULE_EVENT_ONLY, 301), "event_handover": (capi.SCHEDULE_EVENT, 1001)}
 
 
 @pytest.mark.parametrize("schedule", list(SCHEDULES))

@@ -100,3 +100,29 @@ def test_reference_point_source_leakage():
     n, p = drv.batchsize, np.exp(-1)
     assert n == 1000
     assert abs(scores[0] / n - p) / p < 3 * np.sqrt((1 - p) / (p * n))
+
+
+def test_refresh_device_reuploads_tables_in_place():
+    """mmc_world_update through Driver::RefreshDevice: the World is flattened again and uploaded into the existing
+    device world; solving before and after gives the same text, and solving twice accumulates nothing stale."""
+    drv = capi.Driver(text=util.deck_text("three_shells", "surface"))
+    drv.set_options(secondary_capacity=256)
+    drv.solve()
+    first = drv.output()
+    for _ in range(3):
+        drv.refresh_device()
+        drv.solve()
+        assert drv.output() == first
+    assert first == (util.GOLDEN / "three_shells__surface.out").read_text()
+
+
+def test_world_update_rejects_a_different_shape():
+    """mmc_world_update only replaces values: tables of another size need a new world."""
+    a = util.flat_from_xml(util.deck_text("three_shells", "surface"))
+    b = util.flat_from_xml(util.deck_text("leakage_sphere", "surface"))
+    world = util.product_world(a)
+    import ctypes as C
+    other, same = capi.FlatWorld(**b["world"]), capi.FlatWorld(**a["world"])
+    other_desc, same_desc = other.desc(), same.desc()
+    assert capi.load().mmc_world_update(world._handle, C.byref(other_desc)) == capi.ERR_INVALID
+    assert capi.load().mmc_world_update(world._handle, C.byref(same_desc)) == 0
