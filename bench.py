@@ -49,6 +49,14 @@ WORKLOADS = {
         "name": "continuous_temperature (BASELINE configs[4]): CE + S(a,b) slab, cell delta tracking, linear T(x) "
                 "300..600 K, synthetic full-shape tables",
         "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+    "multi_zone": {
+        "name": "multi_zone (BASELINE configs[2], benchmarks/multi_zone.xml): CE + S(a,b), 13 slab segments at "
+                "300..600 K between 14 planes, surface tracking, 202-bin current estimator, synthetic full-shape tables",
+        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+    "broomstick": {
+        "name": "broomstick (BASELINE configs[3], benchmarks/broomstick.xml): CE + S(a,b), cylinder r = 1e-6 along x, "
+                "at most one collision per history, 184 x 239 cosine x energy bins, synthetic full-shape tables",
+        "histories_per_gpu": 1 << 25, "cpu_rate_guess": 4.0e5},
     "multigroup_critical": {
         "name": "multigroup_critical (BASELINE configs[0], SURVEY M1): 1-group infinite medium c=0.25, surface tracking",
         "histories_per_gpu": 1 << 30, "cpu_rate_guess": 4.0e6},
@@ -146,6 +154,11 @@ def deck_text(workload: str, table_dir, histories: int, threads: int) -> str:
         return ce_decks.single_zone_benchmark_deck(table_dir, histories=histories, threads=threads)
     if workload == "continuous_temperature":
         return ce_decks.continuous_temperature_deck(table_dir, histories=histories, threads=threads, n_energy_bins=201)
+    if workload == "multi_zone":
+        return ce_decks.multi_zone_deck(table_dir, histories=histories, threads=threads, n_energy_bins=201)
+    if workload == "broomstick":
+        return ce_decks.broomstick_deck(table_dir, histories=histories, threads=threads, n_energy_bins=238,
+                                        n_cosine_bins=182)
     raise SystemExit(f"unknown workload {workload}")
 
 

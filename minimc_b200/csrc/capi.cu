@@ -513,7 +513,7 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     for (int k = 0; k < batch && status == MMC_OK; k++, pass++) {
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
       const cudaError_t err = launch_event_pass(
-          w->d_blob, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
+          w->d_blob, w->header, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
           b.counter_replicas, tsl, p.stream, mark());
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
       if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "launch_event_pass: %s", cudaGetErrorString(err));

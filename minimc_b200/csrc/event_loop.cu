@@ -24,6 +24,11 @@
 
 #include "kernel_common.cuh"
 
+// 1: the flight kernel's history claims, queue appends and counters are done per warp (no CTA barrier, 8x the
+// atomics); 0: per CTA through shared memory (four barriers).  Measured choice, see DESIGN.md s4.1.
+#ifndef MMC_EV_FLIGHT_WARP_LEVEL
+#define MMC_EV_FLIGHT_WARP_LEVEL 0
+#endif
 #ifndef MMC_EV_FLIGHT_BLOCKS
 #define MMC_EV_FLIGHT_BLOCKS 3
 #endif
@@ -81,14 +86,16 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
 
 template <int kTracking>
 __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_flight_kernel(
-    const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
-    const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
-    BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
+    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
+    const double* __restrict__ bounds, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
+    uint32_t pass, BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
     unsigned long long* scores, unsigned long long* square_scores, unsigned long long* counter_replicas) {
+#if !MMC_EV_FLIGHT_WARP_LEVEL
   __shared__ uint32_t s_totals[3][kWarpsPerBlock];  // per-warp counts: history claims, live slots, S(a,b) slots
   __shared__ unsigned long long s_claim_base;
   __shared__ uint32_t s_queue_base[2];
   __shared__ uint4 s_packed[kWarpsPerBlock];  // per-warp packed counter sums
+#endif
 
   const uint32_t parity = pass & 1u;
   const uint32_t first = blockIdx.x * kThreadsPerBlock;
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = 0;  // chunk counter of this pass's S(a,b) kernel
   if (first >= n) return;  // CTA-uniform
   const bool valid = i < n;
-  const WorldView w(world_g);
+  const WorldView w(world_g, &header);
   const bool has_secondaries = run.secondary_capacity > 1;
 
   if (!valid) p.event = MMC_EV_CAPTURE;
@@ -139,6 +146,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   // ... else a new history: one atomic per CTA claims the indices
   const bool need = valid && !alive;
   const unsigned need_mask = __ballot_sync(kFull, need);
+#if MMC_EV_FLIGHT_WARP_LEVEL
+  unsigned long long claim_base = 0;
+  if (need_mask) {
+    if (lane == 0) {
+      claim_base = *reinterpret_cast<volatile unsigned long long*>(next_history);
+      if (claim_base < run.n_histories) claim_base = atomicAdd(next_history, static_cast<unsigned long long>(__popc(need_mask)));
+    }
+    claim_base = __shfl_sync(kFull, claim_base, 0);
+  }
+  const uint32_t claim_prefix = 0;
+#else
   if (lane == 0) s_totals[0][warp] = __popc(need_mask);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -152,10 +170,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
     s_claim_base = base;
   }
   __syncthreads();
+  uint32_t claim_total;
+  const unsigned long long claim_base = s_claim_base;
+  const uint32_t claim_prefix = warp_prefix(s_totals[0], warp, claim_total);
+#endif
   bool retired = false;
   if (need) {
-    uint32_t total;
-    const uint64_t idx = s_claim_base + warp_prefix(s_totals[0], warp, total) + __popc(need_mask & lanes_below);
+    const uint64_t idx = claim_base + claim_prefix + __popc(need_mask & lanes_below);
     if (idx < run.n_histories) {
       // a new scoring proxy starts empty: FixedSource.cpp:48
       n_pending = 0;
@@ -240,18 +261,34 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   const bool to_tsl = alive && o.need_tsl;
   const unsigned keep_mask = __ballot_sync(kFull, keep);
   const unsigned tsl_mask = __ballot_sync(kFull, to_tsl);
+  // ---- counters: the 0/1-per-lane counters packed four to a word, one warp reduction per word
+  const uint32_t pa = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
+  const uint32_t pb = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
+  const uint32_t pd = c.scores | (c.capacity << 16);  // at most kMaxEstimators + 1 each per lane
+  const uint32_t sa = __reduce_add_sync(kFull, pa), sb = __reduce_add_sync(kFull, pb), sd = __reduce_add_sync(kFull, pd);
+  const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
+#if MMC_EV_FLIGHT_WARP_LEVEL
+  // no CTA barrier anywhere: every warp appends to the queues and adds its counters on its own
+  uint32_t keep_base = 0, tsl_base = 0;
+  if (lane == 0) {
+    if (keep_mask) keep_base = atomicAdd(&q.count[parity ^ 1u], static_cast<unsigned int>(__popc(keep_mask)));
+    if (tsl_mask) tsl_base = atomicAdd(&q.count[2u + parity], static_cast<unsigned int>(__popc(tsl_mask)));
+    unsigned long long* mine = counter_replicas + ((blockIdx.x * kWarpsPerBlock + warp) % kCounterReplicas) * kNumCounters;
+    const uint32_t sums[kNumCounters] = {sb & 0xffu, (sb >> 8) & 0xffu, sa & 0xffu, (sa >> 8) & 0xffu, (sa >> 16) & 0xffu, sa >> 24,
+                                         sd & 0xffffu, ss, 0u, (sb >> 16) & 0xffu, sd >> 16, sb >> 24};
+#pragma unroll
+    for (int k = 0; k < kNumCounters; k++)
+      if (sums[k]) atomicAdd(mine + k, static_cast<unsigned long long>(sums[k]));
+  }
+  keep_base = __shfl_sync(kFull, keep_base, 0);
+  tsl_base = __shfl_sync(kFull, tsl_base, 0);
+  if (keep) q.alive[parity ^ 1u][keep_base + __popc(keep_mask & lanes_below)] = slot;
+  if (to_tsl) q.tsl[tsl_base + __popc(tsl_mask & lanes_below)] = slot;
+#else
   if (lane == 0) {
     s_totals[1][warp] = __popc(keep_mask);
     s_totals[2][warp] = __popc(tsl_mask);
-  }
-  // ---- counters: the 0/1-per-lane counters packed four to a word, one warp reduction per word, no atomics
-  {
-    const uint32_t a = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
-    const uint32_t b = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
-    const uint32_t d = c.scores | (c.capacity << 16);  // at most kMaxEstimators + 1 each per lane
-    const uint32_t sa = __reduce_add_sync(kFull, a), sb = __reduce_add_sync(kFull, b), sd = __reduce_add_sync(kFull, d);
-    const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
-    if (lane == 0) s_packed[warp] = make_uint4(sa, sb, sd, ss);
+    s_packed[warp] = make_uint4(sa, sb, sd, ss);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -281,6 +318,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
   uint32_t total;
   if (keep) q.alive[parity ^ 1u][s_queue_base[0] + warp_prefix(s_totals[1], warp, total) + __popc(keep_mask & lanes_below)] = slot;
   if (to_tsl) q.tsl[s_queue_base[1] + warp_prefix(s_totals[2], warp, total) + __popc(tsl_mask & lanes_below)] = slot;
+#endif
 }
 
 // ThermalScattering::Scatter (ThermalScattering.cpp:159-171) for the slots the flight kernel queued.
@@ -294,8 +332,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
 // Warps walk the queue in chunks of 32 slots; state loads and stores are coalesced over the compacted queue.
 template <bool kSharedSc>
 __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
-    const char* __restrict__ world_g, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
-    uint32_t pass, unsigned long long* counter_replicas) {
+    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ EventState st,
+    const __grid_constant__ EventQueues q, uint32_t pass, unsigned long long* counter_replicas) {
   extern __shared__ __align__(16) char smem[];
   [[maybe_unused]] double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
   char* s_sc = smem + kTslRowBytes;
@@ -307,7 +345,7 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
   const uint32_t n = q.count[2u + parity];
   constexpr uint32_t kWarps = kTslThreads / 32;
   if (blockIdx.x * kWarps * 32u >= n) return;  // CTA-uniform: not even the first warp has work
-  const WorldView w(world_g);
+  const WorldView w(world_g, &header);
   if (kSharedSc) {
     const uint4* src = reinterpret_cast<const uint4*>(world_g + w.h->off_sc_arena);
     uint4* dst = reinterpret_cast<uint4*>(s_sc);
@@ -320,8 +358,8 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
 #else
   ce::SharedRows<kTslThreads, kSharedSc> rows(s_rows, s_sc, w.h->off_sc_arena);
 #endif
-  // warps claim chunks of 32 queue entries from one counter: a scatter takes 20-60 reconstructions, so a static
-  // split leaves the unlucky warps running alone at the end of every pass
+  // warps claim chunks of 32 queue entries from one counter: a scatter takes 10-30 rounds of reconstructions, so a
+  // static split leaves the unlucky warps running alone at the end of every pass (chunks of 64: no faster)
   while (true) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&q.count[4], 32u);
@@ -373,7 +411,7 @@ cudaError_t launch_event_init(const EventState& st, const EventQueues& q, uint32
 }
 
 cudaError_t launch_event_pass(
-    const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
+    const char* world_d, const WorldHeader& header, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
     unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream, cudaEvent_t after_flight) {
@@ -381,11 +419,11 @@ cudaError_t launch_event_pass(
   if (blocks == 0) return cudaSuccess;
   if (run.tracking == MMC_TRACK_CELL_DELTA)
     event_flight_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kThreadsPerBlock, 0, stream>>>(
-        world_d, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
+        world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
   else
     event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kThreadsPerBlock, 0, stream>>>(
-        world_d, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
+        world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
   if (after_flight) cudaEventRecord(after_flight, stream);
   // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queue can feed
@@ -393,9 +431,9 @@ cudaError_t launch_event_pass(
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
   if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
   if (tsl.shared_sc)
-    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(world_d, st, q, pass, counter_replicas);
+    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(world_d, header, st, q, pass, counter_replicas);
   else
-    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, st, q, pass, counter_replicas);
+    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, header, st, q, pass, counter_replicas);
   return cudaGetLastError();
 }
 

@@ -89,7 +89,7 @@ cudaError_t launch_event_init(const EventState& st, const EventQueues& q, uint32
                               unsigned long long* counter_replicas, cudaStream_t stream);
 // one pass = one event of every live slot: the flight kernel, then the S(a,b) kernel over the slots it queued
 cudaError_t launch_event_pass(
-    const char* world_d, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
+    const char* world_d, const WorldHeader& header, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
     unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream,

@@ -24,6 +24,9 @@ struct WorldView {
   const WorldHeader* h;
   __device__ __forceinline__ explicit WorldView(const char* b)
       : base(b), h(reinterpret_cast<const WorldHeader*>(b)) {}
+  // header in kernel-parameter (constant) space: every w.h->off_* becomes a constant-bank operand instead of a
+  // dependent global load in front of each table access
+  __device__ __forceinline__ WorldView(const char* b, const WorldHeader* header) : base(b), h(header) {}
   template <typename T> __device__ __forceinline__ const T* at(uint32_t off) const {
     return reinterpret_cast<const T*>(base + off);
   }

@@ -133,6 +133,28 @@ def test_ce_full_size_tables_properties(tmp_path):
         assert small.output() == port_py.ref_run(path)[0]
 
 
+def test_ce_schedules_agree_at_scale(tmp_path):
+    """Full-shape tables, 3*10^5 histories of single_zone (BASELINE configs[1]) and of continuous_temperature: the
+    event-split schedule (with and without the hand-over of the drain, ragged slot count) and the fused kernel
+    give identical integer tallies and counters -- scheduling never changes a history."""
+    ce_decks.generate_tables(tmp_path, "full")
+    n = 300_000
+    for text in (ce_decks.single_zone_benchmark_deck(tmp_path, histories=n, threads=4),
+                 ce_decks.continuous_temperature_deck(tmp_path, histories=n, threads=4)):
+        results = []
+        for schedule, slots in ((capi.SCHEDULE_FUSED, 0), (capi.SCHEDULE_EVENT, 0), (capi.SCHEDULE_EVENT, 65537),
+                                (capi.SCHEDULE_EVENT_ONLY, 40001)):
+            drv = capi.Driver(text=text)
+            drv.set_options(schedule=schedule, event_slots=slots)
+            scores, squares = drv.solve()
+            c = drv.counters()
+            assert c["n_histories"] == n and c["n_lost"] == c["n_physics_errors"] == c["n_capacity_overflow"] == 0
+            results.append((scores, squares, c))
+        for scores, squares, c in results[1:]:
+            assert np.array_equal(scores, results[0][0]) and np.array_equal(squares, results[0][1])
+            assert c == results[0][2]
+
+
 def test_ce_resample_limit_is_reported(tables):
     """A source far above every table (20 MeV neutron in the slab) still runs; an absurd temperature below every
     partition's grid makes BetaPartition::Evaluate divide 0 by 0 and the resample limit trip: the reference throws
