@@ -29,8 +29,12 @@
 #ifndef MMC_EV_FLIGHT_WARP_LEVEL
 #define MMC_EV_FLIGHT_WARP_LEVEL 0
 #endif
+// flight kernel CTA: threads, and resident CTAs per SM the register allocation is tuned for (768 threads per SM)
+#ifndef MMC_EV_FLIGHT_THREADS
+#define MMC_EV_FLIGHT_THREADS 256
+#endif
 #ifndef MMC_EV_FLIGHT_BLOCKS
-#define MMC_EV_FLIGHT_BLOCKS 3
+#define MMC_EV_FLIGHT_BLOCKS (768 / MMC_EV_FLIGHT_THREADS)
 #endif
 // The S(a,b) kernel runs one persistent CTA per SM.  Measured on B200 (single_zone, hist/s): 768 threads with the
 // mode rows in shared memory 6.90e7; 512 threads with the mode rows in 40 registers per lane 7.18e7 (384: 6.64e7,
@@ -47,7 +51,8 @@ namespace mmc {
 
 namespace {
 
-constexpr int kWarpsPerBlock = kThreadsPerBlock / 32;
+constexpr int kFlightThreads = MMC_EV_FLIGHT_THREADS;
+constexpr int kWarpsPerBlock = kFlightThreads / 32;
 constexpr int kTslThreads = MMC_EV_TSL_THREADS;
 constexpr size_t kTslRowBytes = MMC_EV_TSL_ROWS_IN_REGS ? 0 : 10 * kTslThreads * sizeof(double2);
 
@@ -85,7 +90,7 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
 }
 
 template <int kTracking>
-__global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_flight_kernel(
+__global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_flight_kernel(
     const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
     const double* __restrict__ bounds, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
     uint32_t pass, BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MMC_EV_FLIGHT_BLOCKS) event_
 #endif
 
   const uint32_t parity = pass & 1u;
-  const uint32_t first = blockIdx.x * kThreadsPerBlock;
+  const uint32_t first = blockIdx.x * kFlightThreads;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t i = first + threadIdx.x;
@@ -415,14 +420,14 @@ cudaError_t launch_event_pass(
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
     unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream, cudaEvent_t after_flight) {
-  const uint32_t blocks = (alive_upper_bound + kThreadsPerBlock - 1) / kThreadsPerBlock;
+  const uint32_t blocks = (alive_upper_bound + kFlightThreads - 1) / kFlightThreads;
   if (blocks == 0) return cudaSuccess;
   if (run.tracking == MMC_TRACK_CELL_DELTA)
-    event_flight_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kThreadsPerBlock, 0, stream>>>(
+    event_flight_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kFlightThreads, 0, stream>>>(
         world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
   else
-    event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kThreadsPerBlock, 0, stream>>>(
+    event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
         world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
   if (after_flight) cudaEventRecord(after_flight, stream);

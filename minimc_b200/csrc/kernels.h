@@ -77,7 +77,7 @@ struct EventQueues {
 constexpr int kCounterReplicas = 64;
 
 // array length for n_slots slots: whole CTAs of the flight kernel may read (not use) queue entries past the end
-inline uint32_t event_padded_slots(uint32_t n_slots) { return (n_slots + 255u) & ~255u; }
+inline uint32_t event_padded_slots(uint32_t n_slots) { return (n_slots + 511u) & ~511u; }
 
 struct EventTslConfig {
   uint32_t sm_count = 0;

@@ -13,6 +13,9 @@ echo "== bench reference arm"; timeout 900 python bench.py --impl reference --st
 fi
 echo "== bench"; timeout 1500 python bench.py --gpus 1 --steps 10 --warmup 3 ${BENCH_ARGS:-} 2>$OUT/bench.err | tee $OUT/bench.json
 echo "== bench continuous_temperature"; timeout 900 python bench.py --workload continuous_temperature --steps 5 --warmup 3 --no-multigroup --no-cpu-baseline 2>$OUT/bench_ct.err | tee $OUT/bench_ct.json
+for wl in multi_zone broomstick; do
+echo "== bench $wl"; timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 --no-multigroup --no-cpu-baseline 2>$OUT/bench_$wl.err | tee $OUT/bench_$wl.json
+done
 echo "== bench fused schedule (for comparison)"; MMC_SCHEDULE=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-multigroup --no-cpu-baseline 2>$OUT/bench_fused.err | tee $OUT/bench_fused.json
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv \
