@@ -293,6 +293,25 @@ int mmc_fixed_source_run(
     int32_t n_estimators, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
     const mmc_run_options* options, double* scores, double* square_scores, mmc_counters* counters);
 
+/* Differential-operator sensitivities (Perturbation.cpp:68-84, Sensitivity.cpp:44-58, Particle.cpp:46-53): sensitivity
+ * i is the CurrentTotalCrossSectionSensitivity of estimators[estimator] to the total cross section of nuclide
+ * `nuclide` (TotalCrossSectionPerturbation).  It shares its estimator's bins; every particle accumulates
+ * 1 / GetCollisionProbabilityDensity - distance per Stream in a material that holds the nuclide, and scores
+ * that indirect effect times the estimator's score. */
+typedef struct mmc_sensitivity_desc {
+  int32_t estimator;                /* index into the estimators array */
+  int32_t nuclide;                  /* index of the perturbed nuclide in the world */
+} mmc_sensitivity_desc;
+
+/* mmc_fixed_source_run plus sensitivities: sens_scores / sens_square_scores are the concatenation, in sensitivity
+ * order, of Scorable::scores / square_scores of each Sensitivity (mmc_estimator_size of its estimator each), ADDED to
+ * like scores.  Real-valued sums of fp64 atomics: equal to the reference up to summation order. */
+int mmc_fixed_source_run_sensitivities(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators,
+    int32_t n_estimators, const mmc_sensitivity_desc* sensitivities, int32_t n_sensitivities, uint64_t seed0,
+    uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, double* scores,
+    double* square_scores, double* sens_scores, double* sens_square_scores, mmc_counters* counters);
+
 /* Same, asynchronous on options->stream, with DEVICE tally buffers of exact
  * integer counts (the `current` score is 0 or 1 per event, so Sigma s and
  * Sigma (per-history sum)^2 are integers): d_scores / d_square_scores are

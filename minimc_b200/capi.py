@@ -100,7 +100,7 @@ SCHEDULE_AUTO, SCHEDULE_FUSED, SCHEDULE_EVENT, SCHEDULE_EVENT_ONLY = 0, 1, 2, 3 
 # every symbol include/minimc_b200.h declares
 EXPORTS = (
     "mmc_abi_version", "mmc_last_error", "mmc_device_count", "mmc_world_create", "mmc_world_destroy",
-    "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_device", "mmc_trace_histories",
+    "mmc_estimator_size", "mmc_fixed_source_run", "mmc_fixed_source_run_sensitivities", "mmc_fixed_source_run_device", "mmc_trace_histories",
     "mmc_test_device_math", "mmc_test_geometry",
     "mmc_source_bank_sample", "mmc_generation_run", "mmc_bank_resample",
     "mmc_device_alloc", "mmc_device_free", "mmc_device_zero", "mmc_device_read", "mmc_device_write",

@@ -344,6 +344,15 @@ def slab_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking=None,
     return s
 
 
+def sensitivity_slab_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking=None) -> str:
+    """N4: the single-zone slab with the sensitivity of both currents to the total cross section of
+    hydrogen in water (continuous energy + thermal scattering; with `cell delta` tracking the indirect effect uses
+    the majorant)."""
+    s = slab_deck(table_dir, histories=histories, threads=threads, seed=seed, tracking=tracking, n_energy_bins=8)
+    s = s.replace("    <bins>\n", '    <sensitivities>\n      <perturbation name="h-total"/>\n    </sensitivities>\n    <bins>\n')
+    return s.replace("</estimators>\n", '</estimators>\n<perturbations>\n  <total name="h-total" nuclide="hydrogen in water"/>\n</perturbations>\n')
+
+
 def single_zone_benchmark_deck(table_dir, *, histories=1000000, threads=8, seed=None) -> str:
     """benchmarks/single_zone.xml as shipped (BASELINE configs[1]) with the table paths rewritten: 5 cm slab, global
     constant temperature 450 K, data evaluated at 293.6 K, surface tracking, one `current` estimator on the right

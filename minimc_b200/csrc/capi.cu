@@ -149,6 +149,12 @@ struct mmc_world {
   unsigned int* h_event_counts = nullptr;
   uint64_t last_launches = 0;  // kernels launched by the last event-split run
   double last_flight_ms = 0, last_tsl_ms = 0;  // profile mode: device time of the flight / S(a,b) kernels
+  // sensitivities: per-thread pending entries, device tallies with a pinned mirror
+  SensitivityPending* d_sens_pending = nullptr;
+  size_t sens_pending_bytes = 0;
+  double* d_sens = nullptr;
+  double* h_sens = nullptr;
+  size_t sens_words = 0;
   // k-eigenvalue scratch
   BankSite* d_unordered = nullptr;
   size_t unordered_bytes = 0;
@@ -874,6 +880,9 @@ void mmc_world_destroy(mmc_world* w) {
   scratch_release(w->device, kScratchPending, w->d_pending, w->pending_bytes);
   cudaFree(w->d_bounds);
   cudaFree(w->d_next);
+  cudaFree(w->d_sens_pending);
+  cudaFree(w->d_sens);
+  if (w->h_sens) cudaFreeHost(w->h_sens);
   scratch_release(w->device, kScratchEvent, w->d_event, w->event_bytes);
   if (w->h_event_counts) cudaFreeHost(w->h_event_counts);
   cudaFree(w->d_unordered);
@@ -1002,6 +1011,111 @@ int mmc_bank_resample(const mmc_world* world, const mmc_site* d_slice, uint64_t 
       reinterpret_cast<const BankSite*>(d_slice), slice_first, slice_n, m_total, n_total, first_out, n_out,
       reinterpret_cast<BankSite*>(d_bank_next), reinterpret_cast<unsigned long long*>(d_errors), stream));
   return MMC_OK;
+}
+
+int mmc_fixed_source_run_sensitivities(
+    const mmc_world* world, const mmc_source_desc* source, const mmc_estimator_desc* estimators, int32_t n_estimators,
+    const mmc_sensitivity_desc* sensitivities, int32_t n_sensitivities, uint64_t seed0, uint64_t first_history,
+    uint64_t n_histories, const mmc_run_options* options, double* scores, double* square_scores, double* sens_scores,
+    double* sens_square_scores, mmc_counters* counters) {
+  if (n_sensitivities == 0)
+    return mmc_fixed_source_run(world, source, estimators, n_estimators, seed0, first_history, n_histories, options,
+                                scores, square_scores, counters);
+  if (!world) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  auto* w = const_cast<mmc_world*>(world);
+  if (n_sensitivities < 0 || n_sensitivities > kMaxSensitivities)
+    return fail(MMC_ERR_INVALID, "n_sensitivities %d out of range [0, %d]", n_sensitivities, kMaxSensitivities);
+  if (!sensitivities || !sens_scores || !sens_square_scores)
+    return fail(MMC_ERR_INVALID, "sensitivities / sens_scores / sens_square_scores is NULL");
+  mmc_run_options opt{};
+  if (options) opt = *options;
+  opt.struct_size = sizeof(mmc_run_options);
+  opt.schedule = MMC_SCHEDULE_FUSED;  // the sensitivity proxies live in the fused kernel
+  Prepared p;
+  if (int s = prepare_run(w, source, estimators, n_estimators, seed0, first_history, n_histories, &opt, false, p)) return s;
+  // distinct perturbed nuclides, sensitivity offsets
+  RunSpec& run = p.run;
+  uint64_t sens_bins = 0;
+  for (int i = 0; i < n_sensitivities; i++) {
+    const mmc_sensitivity_desc& sd = sensitivities[i];
+    if (sd.estimator < 0 || sd.estimator >= n_estimators)
+      return fail(MMC_ERR_INVALID, "sensitivity %d: estimator index %d out of range", i, sd.estimator);
+    if (sd.nuclide < 0 || sd.nuclide >= w->header.n_nuclides)
+      return fail(MMC_ERR_INVALID, "sensitivity %d: nuclide index %d out of range", i, sd.nuclide);
+    int k = 0;
+    while (k < run.n_perturbations && run.perturbed_nuclide[k] != sd.nuclide) k++;
+    if (k == run.n_perturbations) {
+      if (k == kMaxPerturbations) return fail(MMC_ERR_INVALID, "more than %d distinct perturbed nuclides", kMaxPerturbations);
+      run.perturbed_nuclide[run.n_perturbations++] = sd.nuclide;
+    }
+    run.sensitivities[i].estimator = sd.estimator;
+    run.sensitivities[i].perturbation = k;
+    run.sensitivities[i].offset = sens_bins;
+    sens_bins += mmc_estimator_size(&estimators[sd.estimator]);
+  }
+  run.n_sensitivities = n_sensitivities;
+  run.sens_pending_capacity = run.pending_capacity * static_cast<uint32_t>(n_sensitivities);
+  MMC_CUDA(cudaSetDevice(w->device));
+  if (n_histories == 0) return MMC_OK;
+  // launch shape of the kPerturb instantiation
+  int per_sm = max_blocks_per_sm(run.tracking, run.continuous_energy != 0, false, run.world_in_smem ? run.world_bytes : 0, true);
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = static_cast<long long>(w->sm_count) * per_sm;
+  const long long useful = static_cast<long long>((n_histories + kThreadsPerBlock - 1) / kThreadsPerBlock);
+  if (blocks > useful) blocks = std::max<long long>(useful, 1);
+  p.cfg.blocks = static_cast<int>(blocks);
+  const size_t threads = static_cast<size_t>(p.cfg.blocks) * kThreadsPerBlock;
+  if (int s = ensure_scratch(w, threads, run.secondary_capacity, run.pending_capacity, p.bounds.size())) return s;
+  const size_t need_pending = threads * run.sens_pending_capacity * sizeof(SensitivityPending);
+  if (need_pending > w->sens_pending_bytes) {
+    cudaFree(w->d_sens_pending);
+    w->d_sens_pending = nullptr;
+    w->sens_pending_bytes = 0;
+    MMC_CUDA(cudaMalloc(&w->d_sens_pending, need_pending));
+    w->sens_pending_bytes = need_pending;
+  }
+  // device tallies: [sens scores | sens squares] doubles, [scores | squares | counters] integers
+  const uint64_t total_bins = run.total_bins;
+  constexpr size_t kCounterWords = sizeof(mmc_counters) / sizeof(unsigned long long);
+  const size_t words = 2 * sens_bins + 2 * total_bins + kCounterWords;
+  if (words > w->sens_words) {
+    cudaFree(w->d_sens);
+    if (w->h_sens) cudaFreeHost(w->h_sens);
+    w->d_sens = w->h_sens = nullptr;
+    w->sens_words = 0;
+    MMC_CUDA(cudaMalloc(&w->d_sens, words * sizeof(double)));
+    MMC_CUDA(cudaMallocHost(&w->h_sens, words * sizeof(double)));
+    w->sens_words = words;
+  }
+  cudaStream_t stream = p.stream;
+  MMC_CUDA(cudaMemsetAsync(w->d_sens, 0, words * sizeof(double), stream));
+  if (!p.bounds.empty())
+    MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+  MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), stream));
+  SensitivityIO io;
+  io.pending = w->d_sens_pending;
+  io.scores = w->d_sens;
+  io.square_scores = w->d_sens + sens_bins;
+  auto* d_tally = reinterpret_cast<unsigned long long*>(w->d_sens + 2 * sens_bins);
+  auto* d_counters = reinterpret_cast<mmc_counters*>(d_tally + 2 * total_bins);
+  w->last_launches = 1;
+  MMC_CUDA(launch_fixed_source(p.cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending, w->d_next, d_tally,
+                               d_tally + total_bins, d_counters, nullptr, stream, nullptr, &io));
+  MMC_CUDA(cudaMemcpyAsync(w->h_sens, w->d_sens, words * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  MMC_CUDA(cudaStreamSynchronize(stream));
+  for (uint64_t i = 0; i < sens_bins; i++) {
+    sens_scores[i] += w->h_sens[i];
+    sens_square_scores[i] += w->h_sens[sens_bins + i];
+  }
+  const auto* h_tally = reinterpret_cast<const unsigned long long*>(w->h_sens + 2 * sens_bins);
+  for (uint64_t i = 0; i < total_bins; i++) {
+    scores[i] += static_cast<double>(h_tally[i]);
+    square_scores[i] += static_cast<double>(h_tally[total_bins + i]);
+  }
+  mmc_counters h_counters{};
+  std::memcpy(&h_counters, h_tally + 2 * total_bins, sizeof(mmc_counters));
+  if (counters) *counters = h_counters;
+  return status_from_counters(h_counters);
 }
 
 int mmc_fixed_source_run(

@@ -62,12 +62,20 @@ __device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t
 // atomic per warp claims the slots, each parent's run is contiguous, and
 // (count, start) per parent let order_bank_kernel restore the deterministic
 // (parent index, creation ordinal) order.
-template <int kTracking, bool kCE, bool kGeneration>
+//
+// kPerturb = true: differential-operator sensitivities (Perturbation.cpp, Sensitivity.cpp).  Every particle carries
+// one indirect effect per perturbation, reset when the particle is taken from the bank (FixedSource.cpp:65) and
+// grown by every Stream (transport.cuh perturb_stream); where an estimator scores, each of its sensitivities scores
+// indirect effect x estimator score into the sensitivity's per-history pending table (ScorableProxy::Score,
+// Scorable.cpp:81-99), committed -- sum and sum squared -- when the history ends (CommitHistory, :101-106).  These
+// tallies are real-valued: fp64 atomics, order-dependent in the last bits exactly as the reference's own worker merge.
+template <int kTracking, bool kCE, bool kGeneration, bool kPerturb>
 __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM : MMC_MG_BLOCKS_PER_SM) fixed_source_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
     unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters,
-    const __grid_constant__ GenerationIO bank, const __grid_constant__ ResumeIO resume) {
+    const __grid_constant__ GenerationIO bank, const __grid_constant__ ResumeIO resume,
+    const __grid_constant__ SensitivityIO sens) {
   extern __shared__ __align__(16) char smem[];
   const WorldView w(stage_world(world_g, run.world_bytes, run.world_in_smem != 0, smem));
 
@@ -84,6 +92,26 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
   dq.count = 0;
   uint2* pending = pending_scratch + scratch * run.pending_capacity;
   uint32_t n_pending = 0;
+  // sensitivities: the particle's indirect effects and the history's pending (bin, sum) entries
+  double indirect[kPerturb ? kMaxPerturbations : 1];
+  SensitivityPending* sens_pending = kPerturb ? sens.pending + scratch * run.sens_pending_capacity : nullptr;
+  uint32_t n_sens_pending = 0;
+  const PerturbContext pc{run.perturbed_nuclide, run.n_perturbations, indirect};
+  auto reset_indirect = [&]() {
+    if (kPerturb)
+      for (int k = 0; k < kMaxPerturbations; k++) indirect[k] = 0.0;
+  };
+  auto commit_sensitivities = [&]() {  // ScorableProxy::CommitHistory of every sensitivity proxy
+    if (kPerturb) {
+      for (uint32_t k = 0; k < n_sens_pending; k++) {
+        const SensitivityPending e = sens_pending[k];
+        atomicAdd(sens.scores + e.bin, e.sum);
+        atomicAdd(sens.square_scores + e.bin, __dmul_rn(e.sum, e.sum));
+      }
+      n_sens_pending = 0;
+    }
+  };
+  reset_indirect();
 
   Particle p;
   p.event = MMC_EV_CAPTURE;  // "dead": forces a refill
@@ -118,6 +146,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
       // bank.back(): FixedSource.cpp:63-71
       dq.count--;
       load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
+      reset_indirect();  // bank.back().SetPerturbations(perturbations)
       alive = true;
       c.births++;
     }
@@ -151,10 +180,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
         w_next += n;
       }
       if (need) {
+        commit_sensitivities();  // the previous history of this lane is over
         if (valid) {
           // scoring_proxy of the previous history is committed (incrementally);
           // a new proxy starts empty: FixedSource.cpp:48
           n_pending = 0;
+          reset_indirect();
           history = idx;
           if (kGeneration) load_site(bank.in[idx], p);
           else if (sample_source(run.source, run.seed0 + run.first_history + idx, p, true)) owed |= 2u;
@@ -190,7 +221,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
           p.event = MMC_EV_LEAK;
         }
       }
-      if (p.cell >= 0) transport_step<kTracking, kCE, true>(w, p, dq, o);
+      if (p.cell >= 0) transport_step<kTracking, kCE, true, false, kPerturb>(w, p, dq, o, &pc);
       if (o.need_direction) owed |= 1u;
       count_event(c, p, o);
     }
@@ -248,9 +279,33 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
           atomicAdd(scores + bin, static_cast<unsigned long long>(__popc(peers)));
           atomicAdd(square_scores + bin, static_cast<unsigned long long>(sq));
         }
+        if (kPerturb) {
+          // CurrentTotalCrossSectionSensitivity::GetScore = indirect effect x estimator score (= 1 here);
+          // ScorableProxy::Score skips a zero score and otherwise adds to the history's entry of the bin
+          for (int32_t si = 0; si < run.n_sensitivities; si++) {
+            const SensitivitySpec& sp = run.sensitivities[si];
+            if (sp.estimator != e) continue;
+            const double value = indirect[sp.perturbation];
+            if (value == 0) continue;
+            const uint32_t sens_bin = static_cast<uint32_t>(sp.offset + (bin - run.estimators[e].offset));
+            uint32_t slot_i = 0;
+            for (; slot_i < n_sens_pending; slot_i++)
+              if (sens_pending[slot_i].bin == sens_bin) break;
+            if (slot_i < n_sens_pending) {
+              sens_pending[slot_i].sum = __dadd_rn(sens_pending[slot_i].sum, value);
+            } else if (n_sens_pending < run.sens_pending_capacity) {
+              sens_pending[n_sens_pending].bin = sens_bin;
+              sens_pending[n_sens_pending].sum = value;
+              n_sens_pending++;
+            } else {
+              c.capacity++;
+            }
+          }
+        }
       }
     }
   }
+  commit_sensitivities();
 
   flush_counter(&counters->n_histories, c.histories);
   flush_counter(&counters->n_births, c.births);
@@ -547,22 +602,25 @@ cudaError_t launch_test_math(int fn, const double* x_d, double* out0_d, double* 
 
 // ------------------------------------------------------------------ launchers
 namespace {
-// picks the instantiation for (tracking, energy mode, fixed source | generation)
-template <typename F> auto dispatch_history_kernel(int tracking, bool ce, bool generation, F&& f) {
+// picks the instantiation for (tracking, energy mode, fixed source | generation | fixed source with sensitivities)
+template <typename F> auto dispatch_history_kernel(int tracking, bool ce, bool generation, bool perturb, F&& f) {
+  const bool delta = tracking == MMC_TRACK_CELL_DELTA;
   if (generation) {
-    if (ce) {
-      if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, true>);
-      return f(fixed_source_kernel<MMC_TRACK_SURFACE, true, true>);
-    }
-    if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, true>);
-    return f(fixed_source_kernel<MMC_TRACK_SURFACE, false, true>);
+    if (ce) return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, true, false>)
+                         : f(fixed_source_kernel<MMC_TRACK_SURFACE, true, true, false>);
+    return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, true, false>)
+                 : f(fixed_source_kernel<MMC_TRACK_SURFACE, false, true, false>);
   }
-  if (ce) {
-    if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, false>);
-    return f(fixed_source_kernel<MMC_TRACK_SURFACE, true, false>);
+  if (perturb) {
+    if (ce) return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, false, true>)
+                         : f(fixed_source_kernel<MMC_TRACK_SURFACE, true, false, true>);
+    return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, false, true>)
+                 : f(fixed_source_kernel<MMC_TRACK_SURFACE, false, false, true>);
   }
-  if (tracking == MMC_TRACK_CELL_DELTA) return f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, false>);
-  return f(fixed_source_kernel<MMC_TRACK_SURFACE, false, false>);
+  if (ce) return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, false, false>)
+                       : f(fixed_source_kernel<MMC_TRACK_SURFACE, true, false, false>);
+  return delta ? f(fixed_source_kernel<MMC_TRACK_CELL_DELTA, false, false, false>)
+               : f(fixed_source_kernel<MMC_TRACK_SURFACE, false, false, false>);
 }
 }  // namespace
 
@@ -570,17 +628,18 @@ cudaError_t launch_fixed_source(
     const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
     uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
     unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream,
-    const ResumeIO* resume) {
+    const ResumeIO* resume, const SensitivityIO* sensitivity) {
   const size_t smem = run.world_in_smem ? run.world_bytes : 0;
   const GenerationIO io = generation ? *generation : GenerationIO{};
   const ResumeIO rs = resume ? *resume : ResumeIO{};
-  return dispatch_history_kernel(run.tracking, run.continuous_energy != 0, generation != nullptr, [&](auto kernel) -> cudaError_t {
+  const SensitivityIO se = sensitivity ? *sensitivity : SensitivityIO{};
+  return dispatch_history_kernel(run.tracking, run.continuous_energy != 0, generation != nullptr, sensitivity != nullptr, [&](auto kernel) -> cudaError_t {
     if (smem > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
     kernel<<<cfg.blocks, kThreadsPerBlock, smem, stream>>>(
-        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io, rs);
+        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io, rs, se);
     return cudaGetLastError();
   });
 }
@@ -600,8 +659,8 @@ cudaError_t launch_trace(
   return go(trace_kernel<MMC_TRACK_SURFACE, false>);
 }
 
-int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem) {
-  return dispatch_history_kernel(tracking, continuous_energy, generation, [&](auto kernel) {
+int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem, bool perturb) {
+  return dispatch_history_kernel(tracking, continuous_energy, generation, perturb, [&](auto kernel) {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreadsPerBlock, smem);
     return n;

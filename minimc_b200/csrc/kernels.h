@@ -59,6 +59,18 @@ struct EventState {
 };
 constexpr size_t kEventStateBytesPerSlot = 8 * 8 + 8 * 4;
 
+// Sensitivity tallies of a run with perturbations (fused kernel, kPerturb): real-valued, fp64 atomics.
+struct SensitivityPending {
+  uint32_t bin;  // index into the concatenated sensitivity tallies
+  uint32_t pad;
+  double sum;    // this history's score in that bin so far
+};
+struct SensitivityIO {
+  SensitivityPending* pending = nullptr;  // [threads][RunSpec::sens_pending_capacity]
+  double* scores = nullptr;               // [total sensitivity bins]
+  double* square_scores = nullptr;
+};
+
 // Hand-over from the event-split schedule to the fused kernel (the tail of a run, when too few histories are alive
 // to fill the GPU and every pass costs its launch latency): thread t < n adopts slot slots[t] -- its particle, pending
 // table and secondary deque -- and runs it, and any history it can still claim, to the end.
@@ -103,9 +115,9 @@ cudaError_t launch_fixed_source(
     const LaunchConfig& cfg, const char* world_d, const RunSpec& run, const double* bounds_d, BankSite* site_scratch,
     uint2* pending_scratch, unsigned long long* next_history, unsigned long long* scores,
     unsigned long long* square_scores, mmc_counters* counters, const GenerationIO* generation, cudaStream_t stream,
-    const ResumeIO* resume = nullptr);
+    const ResumeIO* resume = nullptr, const SensitivityIO* sensitivity = nullptr);
 
 // occupancy query for the fused kernel
-int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem);
+int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem, bool perturb = false);
 
 }  // namespace mmc

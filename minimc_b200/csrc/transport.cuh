@@ -446,11 +446,33 @@ __device__ inline void collide_multigroup(
 
 namespace mmc {
 
+// TotalCrossSectionPerturbation::Stream (Perturbation.cpp:68-80), called by Particle::Stream (Particle.cpp:46-53)
+// before the position moves: every perturbation whose nuclide is in the material the particle streams through
+// adds 1 / GetCollisionProbabilityDensity(p) - distance to its indirect effect.  GetCollisionProbabilityDensity is the
+// MICROSCOPIC total (surface tracking) or majorant (cell delta tracking) of the material, without the number density
+// (TransportMethod.cpp:79-82,124-127): reproduced as it is.
+struct PerturbContext {
+  const int32_t* perturbed_nuclide;  // RunSpec::perturbed_nuclide
+  int32_t n;
+  double* indirect;                  // the particle's indirect effects, one per perturbation
+};
+
+__device__ __forceinline__ void perturb_stream(const WorldView& w, const PerturbContext& pc, int32_t mat, double micro, double distance) {
+  const int32_t* nb = w.at<int32_t>(w.h->off_mat_nuc_begin);
+  const int32_t* ni = w.at<int32_t>(w.h->off_mat_nuc_index);
+  for (int32_t k = 0; k < pc.n; k++) {
+    bool present = false;
+    for (int32_t j = nb[mat]; j < nb[mat + 1]; j++) present = present || ni[j] == pc.perturbed_nuclide[k];
+    if (present) pc.indirect[k] = __dadd_rn(pc.indirect[k], __dsub_rn(__ddiv_rn(1.0, micro), distance));
+  }
+}
+
 // One iteration of SurfaceTracking::Transport (TransportMethod.cpp:56-75) or
 // CellDeltaTracking::Transport (TransportMethod.cpp:92-120).  kCE selects the
 // Continuous (true) or Multigroup (false) Interaction of the world's nuclides.
-template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false>
-__device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out) {
+template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false, bool kPerturb = false>
+__device__ __forceinline__ void transport_step(
+    const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out, const PerturbContext* pc = nullptr) {
   out.secondaries = 0;
   out.need_direction = false;
   out.need_tsl = false;
@@ -490,6 +512,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
   if (kTracking == MMC_TRACK_SURFACE) cross = !(d_coll < d_surf);
   else cross = d_surf < d_coll;
   if (cross) {
+    if (kPerturb) perturb_stream(w, *pc, mat, majorant, __dadd_rn(d_surf, 2.220446049250313e-15));
     stream(p, __dadd_rn(d_surf, 2.220446049250313e-15));  // constants::nudge = 10 * epsilon
     p.cell = find_cell(w, p.px, p.py, p.pz);
     p.surface = nearest;
@@ -514,6 +537,7 @@ __device__ __forceinline__ void transport_step(const WorldView& w, Particle& p, 
       }
       real = p.rng.canonical() < __ddiv_rn(micro, majorant);
     }
+    if (kPerturb) perturb_stream(w, *pc, mat, majorant, d_coll);
     stream(p, d_coll);
     if (real) {
       if (kCE) ce::collide_continuous<kDeferTsl>(w, p, mat, dq, out, ev);

@@ -11,6 +11,16 @@
 namespace mmc {
 
 constexpr int kMaxEstimators = 16;
+constexpr int kMaxPerturbations = 4;   // distinct perturbed nuclides per run
+constexpr int kMaxSensitivities = 16;  // (estimator, perturbation) pairs per run
+
+// Sensitivity of a `current` estimator to the total cross section of one nuclide
+// (CurrentTotalCrossSectionSensitivity, Sensitivity.cpp:44-58): shares the estimator's bins.
+struct SensitivitySpec {
+  int32_t estimator;     // index into RunSpec::estimators
+  int32_t perturbation;  // index into RunSpec::perturbed_nuclide
+  uint64_t offset;       // first bin of this sensitivity in the concatenated sensitivity tallies
+};
 
 struct BinsSpec {
   int32_t kind;        // mmc_bins_kind
@@ -145,6 +155,13 @@ struct RunSpec {
   uint32_t world_bytes;         // size of the world blob (multiple of 16)
   uint32_t world_in_smem;       // 1: kernels stage the blob into shared memory
   uint32_t continuous_energy;   // 1: the world's nuclides are Continuous (n_groups == 0)
+  // differential-operator sensitivities (Perturbation.cpp, Sensitivity.cpp); n_sensitivities == 0: none
+  int32_t n_perturbations;
+  int32_t n_sensitivities;
+  int32_t perturbed_nuclide[kMaxPerturbations];  // TotalCrossSectionPerturbation::nuclide
+  SensitivitySpec sensitivities[kMaxSensitivities];
+  uint32_t sens_pending_capacity;  // per-history (bin, sum) entries of the sensitivity proxies
+  uint32_t pad_sens;
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.

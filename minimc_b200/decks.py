@@ -78,6 +78,10 @@ def _estimators(estimators):
     s = "<estimators>\n"
     for e in estimators:
         s += f'  <current name={quoteattr(e["name"])} surface={quoteattr(e["surface"])}>\n'
+        if e.get("sensitivities"):
+            s += "    <sensitivities>\n"
+            s += "".join(f"      <perturbation name={quoteattr(n)}/>\n" for n in e["sensitivities"])
+            s += "    </sensitivities>\n"
         if e.get("cosine") or e.get("energy"):
             s += "    <bins>\n"
             if e.get("cosine"):
@@ -90,7 +94,15 @@ def _estimators(estimators):
     return s + "</estimators>\n"
 
 
-def _deck(general, groups, nuclides, materials, surfaces, cells, problem, estimators):
+def _perturbations(perturbations):
+    """perturbations: list of (name, nuclide) -> <perturbations><total .../></perturbations>."""
+    if not perturbations:
+        return ""
+    return ("<perturbations>\n" + "".join(f"  <total name={quoteattr(n)} nuclide={quoteattr(nuc)}/>\n" for n, nuc in perturbations)
+            + "</perturbations>\n")
+
+
+def _deck(general, groups, nuclides, materials, surfaces, cells, problem, estimators, perturbations=None):
     return (
         '<minimc\n  xmlns:xsi="http://www.w3.org/2001/XMLSchema-instance"\n'
         '  xsi:noNamespaceSchemaLocation="minimc.xsd">\n'
@@ -99,7 +111,7 @@ def _deck(general, groups, nuclides, materials, surfaces, cells, problem, estima
         + "<materials>\n" + "".join(materials) + "</materials>\n"
         + "<surfaces>\n" + "".join(surfaces) + "</surfaces>\n"
         + "<cells>\n" + "".join(cells) + "</cells>\n"
-        + problem + _estimators(estimators) + "</minimc>\n")
+        + problem + _estimators(estimators) + _perturbations(perturbations) + "</minimc>\n")
 
 
 def _material(name, aden, nuclides):
@@ -151,7 +163,7 @@ THREE_SHELL_ESTIMATORS = [
 ]
 
 
-def three_shells(histories=100000, threads=2, seed=None, tracking=None, estimators=None):
+def three_shells(histories=100000, threads=2, seed=None, tracking=None, estimators=None, perturbations=None):
     """M2: two groups, two-nuclide water, three concentric shells (test/multigroup.xml); `estimators`
     defaults to none as in the reference file, THREE_SHELL_ESTIMATORS reproduces golden G2."""
     return _deck(
@@ -168,7 +180,23 @@ def three_shells(histories=100000, threads=2, seed=None, tracking=None, estimato
          _cell("inner shell", "water", [("inner shell", "+1"), ("middle shell", "-1")]),
          _cell("outer shell", "hydrogen", [("middle shell", "+1"), ("outer shell", "-1")]),
          _cell(None, None, [("outer shell", "+1")])],
-        _source(), estimators)
+        _source(), estimators, perturbations)
+
+
+# N4: differential-operator sensitivities of the three-shell currents to the total cross sections of
+# hydrogen (in every material) and oxygen (in the water shell only)
+SENSITIVITY_PERTURBATIONS = [("h-total", "hydrogen"), ("o-total", "oxygen")]
+SENSITIVITY_ESTIMATORS = [
+    dict(THREE_SHELL_ESTIMATORS[0], sensitivities=["h-total", "o-total"]),
+    THREE_SHELL_ESTIMATORS[1],
+    dict(THREE_SHELL_ESTIMATORS[2], sensitivities=["o-total"]),
+]
+
+
+def sensitivity_shells(histories=20000, threads=2, seed=None, tracking=None):
+    """three_shells with sensitivities of the inner and outer currents to total cross-section perturbations."""
+    return three_shells(histories=histories, threads=threads, seed=seed, tracking=tracking,
+                        estimators=SENSITIVITY_ESTIMATORS, perturbations=SENSITIVITY_PERTURBATIONS)
 
 
 def fissile_slab(histories=20000, threads=2, seed=None, tracking=None):
@@ -288,6 +316,8 @@ def k_slab(histories=20000, threads=2, inactive=3, active=6, tracking=None):
 
 
 KDECKS = {"k_unity": k_unity, "k_infinite": k_infinite, "k_slab": k_slab}
+
+SENSITIVITY_DECKS = {"sensitivity_shells": sensitivity_shells}
 
 DECKS = {
     "critical": critical,

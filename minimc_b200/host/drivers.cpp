@@ -88,11 +88,10 @@ std::unique_ptr<Driver> Driver::CreateFromString(const std::string& xml_text) {
 }
 
 Driver::Driver(const xml::Node& root)
-    : world{root}, batchsize{std::stoull(GeneralChild(root, "histories").text())}, seed{ParseSeed(root)},
-      init_estimator_set{root.child("estimators"), world, static_cast<Real>(batchsize)},
+    : world{root}, perturbations{root.child("perturbations"), world},
+      batchsize{std::stoull(GeneralChild(root, "histories").text())}, seed{ParseSeed(root)},
+      init_estimator_set{root.child("estimators"), world, perturbations, static_cast<Real>(batchsize)},
       threads{std::stoul(GeneralChild(root, "threads").text())}, tracking{ParseTracking(root, world)} {
-  if (const xml::Node* p = root.child("perturbations"); p && !p->children().empty())
-    throw std::runtime_error(p->path() + ": perturbations are not implemented on the GPU path");
   run_options.struct_size = sizeof(mmc_run_options);
   run_options.device = -1;
   run_options.tracking = tracking;
@@ -129,23 +128,42 @@ EstimatorSet FixedSource::Solve() {
   const uint64_t last = static_cast<uint64_t>(rank + 1) * batchsize / static_cast<uint64_t>(world_size);
   std::vector<double> scores(result.total_bins(), 0.0), square_scores(result.total_bins(), 0.0);
   run_options.tracking = tracking;
-  const int status = mmc_fixed_source_run(
-      device_world()->handle, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()), seed, first,
-      last - first, &run_options, scores.data(), square_scores.data(), &counters);
+  // sensitivities (Estimator::sensitivities): (estimator, perturbed nuclide) pairs, tallies concatenated in this order
+  std::vector<mmc_sensitivity_desc> sensitivities;
+  size_t sensitivity_bins = 0;
+  for (size_t e = 0; e < result.estimators.size(); e++)
+    for (const Sensitivity& s : result.estimators[e].sensitivities) {
+      sensitivities.push_back(mmc_sensitivity_desc{static_cast<int32_t>(e), static_cast<int32_t>(s.nuclide)});
+      sensitivity_bins += s.scores.size();
+    }
+  std::vector<double> sens_scores(sensitivity_bins, 0.0), sens_square_scores(sensitivity_bins, 0.0);
+  const int status = mmc_fixed_source_run_sensitivities(
+      device_world()->handle, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()),
+      sensitivities.data(), static_cast<int32_t>(sensitivities.size()), seed, first, last - first, &run_options,
+      scores.data(), square_scores.data(), sens_scores.data(), sens_square_scores.data(), &counters);
   if (status != MMC_OK) ThrowLastError("mmc_fixed_source_run", status);
-  size_t offset = 0;
+  size_t offset = 0, sens_offset = 0;
   for (Estimator& e : result.estimators) {
     for (size_t i = 0; i < e.scores.size(); i++) {
       e.scores[i] += scores[offset + i];
       e.square_scores[i] += square_scores[offset + i];
     }
     offset += e.scores.size();
+    for (Sensitivity& s : e.sensitivities) {
+      for (size_t i = 0; i < s.scores.size(); i++) {
+        s.scores[i] += sens_scores[sens_offset + i];
+        s.square_scores[i] += sens_square_scores[sens_offset + i];
+      }
+      sens_offset += s.scores.size();
+    }
   }
   return result;
 }
 
 void FixedSource::RunDevice(
     uint64_t first, uint64_t count, uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters, void* stream) {
+  if (init_estimator_set.total_sensitivities())
+    throw std::runtime_error("sensitivities are real-valued tallies: use Solve(), not the integer device-buffer run");
   if (device_estimators_.empty() && !init_estimator_set.estimators.empty()) device_estimators_ = FlattenEstimators(init_estimator_set);
   mmc_run_options options = run_options;
   options.tracking = tracking;

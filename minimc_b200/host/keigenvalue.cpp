@@ -68,6 +68,8 @@ KEigenvalue::KEigenvalue(const xml::Node& root)
       last_active{last_inactive + KNode(root).attribute_ull("active")}, source{InitialSource(root)} {}
 
 EstimatorSet KEigenvalue::Solve() {
+  if (init_estimator_set.total_sensitivities())
+    throw std::runtime_error("/minimc/estimators: sensitivities are implemented for fixed-source problems only");
   if (world_size != 1)
     throw std::runtime_error("KEigenvalue::Solve: multi-process runs are driven by minimc_b200.distributed (NCCL bank exchange)");
   const mmc_world* w = device_world_handle();

@@ -177,6 +177,7 @@ public:
   explicit World(const xml::Node& root);
   bool HasConstantTemperature() const noexcept { return temperature.IsConstant(); }
   size_t FindSurfaceIndexByName(const std::string& name) const;  // throws like World::FindSurfaceByName
+  size_t FindNuclideIndexByName(const std::string& name) const;  // throws like World::FindNuclideByName
   bool IsMultigroup() const { return !nuclides.empty() ? nuclides.front().multigroup.has_value() : multigroup_groups > 0; }
   std::vector<CSGSurface> surfaces;
   std::vector<Nuclide> nuclides;
@@ -219,22 +220,46 @@ public:
 };
 
 // Scorable + Estimator + CurrentEstimator (Scorable.cpp, Estimator.cpp:21-151)
+// TotalCrossSectionPerturbation (Perturbation.cpp:44-84): the only perturbation the schema allows
+struct Perturbation {
+  std::string name;
+  size_t nuclide = 0;  // index into World::nuclides
+};
+
+// PerturbationSet (Perturbation.cpp:88-128)
+class PerturbationSet {
+public:
+  PerturbationSet() = default;
+  PerturbationSet(const xml::Node* perturbations_node, const World& world);
+  const Perturbation& FindPerturbationByName(const std::string& name) const;
+  std::vector<Perturbation> perturbations;
+};
+
+// CurrentTotalCrossSectionSensitivity (Sensitivity.cpp:44-58): a Scorable over its estimator's bins
+struct Sensitivity {
+  std::string name;  // estimator name + "::" + perturbation name (Scorable.cpp:22-29)
+  size_t nuclide = 0;
+  std::vector<Real> scores, square_scores;
+};
+
 class Estimator {
 public:
-  Estimator(const xml::Node& estimator_node, const World& world);
+  Estimator(const xml::Node& estimator_node, const World& world, const PerturbationSet& perturbations);
   std::string to_string(Real total_weight) const noexcept;
   Estimator& operator+=(const Estimator& other) noexcept;
   std::string name;
   ParticleBins bins;
   size_t surface = 0;
   std::vector<Real> scores, square_scores;
+  std::vector<Sensitivity> sensitivities;
 };
 
 // EstimatorSet (Estimator.cpp:155-231)
 class EstimatorSet {
 public:
   EstimatorSet() = default;
-  EstimatorSet(const xml::Node* estimators_node, const World& world, Real total_weight);
+  EstimatorSet(const xml::Node* estimators_node, const World& world, const PerturbationSet& perturbations, Real total_weight);
+  size_t total_sensitivities() const noexcept;
   const Estimator& FindEstimatorByName(const std::string& name) const;
   std::string to_string() const noexcept;
   EstimatorSet& operator+=(const EstimatorSet& other);
@@ -265,6 +290,7 @@ public:
   virtual EstimatorSet Solve() = 0;
 
   const World world;
+  const PerturbationSet perturbations;  // Driver.hpp:35-37
   const uint64_t batchsize;
   const uint64_t seed;
   const EstimatorSet init_estimator_set;

@@ -469,6 +469,15 @@ size_t World::FindSurfaceIndexByName(const std::string& name) const {
   return static_cast<size_t>(it - surfaces.cbegin());
 }
 
+size_t World::FindNuclideIndexByName(const std::string& name) const {
+  const auto it = std::find_if(nuclides.cbegin(), nuclides.cend(), [&](const Nuclide& n) { return n.name == name; });
+  if (it == nuclides.cend())
+    throw std::runtime_error(
+        "Nuclide \"" + name + "\" not found. Must be one of: [" +
+        QuotedNames(nuclides, [](const Nuclide& n) { return n.name; }) + "]");
+  return static_cast<size_t>(it - nuclides.cbegin());
+}
+
 // --------------------------------------------------------------------- source
 Source::Source(const xml::Node& source_node) {
   // Distribution<T>::Create, Source.cpp:28-101
@@ -567,21 +576,45 @@ std::string ParticleBins::to_string() const noexcept {
   return result;
 }
 
+// ---------------------------------------------------------------- perturbations
+PerturbationSet::PerturbationSet(const xml::Node* perturbations_node, const World& world) {
+  // PerturbationSet::PerturbationSet + Perturbation::Create (Perturbation.cpp:22-34,90-99)
+  if (!perturbations_node) return;
+  for (const auto& node : perturbations_node->children()) {
+    if (node->name() != "total") throw std::runtime_error(node->path() + ": unknown perturbation type");
+    perturbations.push_back(Perturbation{node->attribute("name"), world.FindNuclideIndexByName(node->attribute("nuclide"))});
+  }
+}
+
+const Perturbation& PerturbationSet::FindPerturbationByName(const std::string& name) const {
+  // Perturbation.cpp:101-119
+  const auto it = std::find_if(perturbations.cbegin(), perturbations.cend(), [&](const Perturbation& p) { return p.name == name; });
+  if (it == perturbations.cend())
+    throw std::runtime_error(
+        "Perturbation \"" + name + "\" not found. Must be one of: [" +
+        QuotedNames(perturbations, [](const Perturbation& p) { return p.name; }) + "]");
+  return *it;
+}
+
 // ------------------------------------------------------------------ estimators
-Estimator::Estimator(const xml::Node& estimator_node, const World& world)
+Estimator::Estimator(const xml::Node& estimator_node, const World& world, const PerturbationSet& perturbations)
     : name{estimator_node.attribute("name")}, bins{estimator_node.child("bins")},
       surface{world.FindSurfaceIndexByName(estimator_node.attribute("surface"))}, scores(bins.size(), 0),
       square_scores(bins.size(), 0) {
   if (estimator_node.name() != "current") throw std::runtime_error(estimator_node.path() + ": unknown estimator type");
-  if (const xml::Node* s = estimator_node.child("sensitivities"); s && !s->children().empty())
-    throw std::runtime_error(s->path() + ": sensitivities are not implemented on the GPU path");
+  // Estimator::Estimator + Sensitivity::Create (Estimator.cpp:83-92, Sensitivity.cpp:13-21)
+  if (const xml::Node* sensitivities_node = estimator_node.child("sensitivities"))
+    for (const auto& node : sensitivities_node->children()) {
+      const Perturbation& perturbation = perturbations.FindPerturbationByName(node->attribute("name"));
+      sensitivities.push_back(Sensitivity{
+          name + "::" + perturbation.name, perturbation.nuclide, std::vector<Real>(bins.size(), 0),
+          std::vector<Real>(bins.size(), 0)});
+    }
 }
 
-std::string Estimator::to_string(Real total_weight) const noexcept {
-  // Estimator::to_string + Scorable::GetScoreAsString (Estimator.cpp:48-57, Scorable.cpp:51-70)
-  std::string result;
-  result += name + "\n" + std::string(name.size(), '=') + "\n\n";
-  result += bins.to_string();
+namespace {
+// Scorable::GetScoreAsString, Scorable.cpp:51-70
+std::string ScoreAsString(const std::vector<Real>& scores, const std::vector<Real>& square_scores, Real total_weight) {
   std::stringstream sstream;
   sstream << "mean\n----\n";
   sstream << std::scientific;
@@ -591,7 +624,19 @@ std::string Estimator::to_string(Real total_weight) const noexcept {
   for (size_t i = 0; i < scores.size(); i++)
     sstream << std::sqrt(square_scores[i] - scores[i] * scores[i] / total_weight) / total_weight << ", ";
   sstream << "\n\n";
-  return result + sstream.str();
+  return sstream.str();
+}
+}  // namespace
+
+std::string Estimator::to_string(Real total_weight) const noexcept {
+  // Estimator::to_string (Estimator.cpp:48-57) and Sensitivity::to_string (Sensitivity.cpp:25-28)
+  std::string result;
+  result += name + "\n" + std::string(name.size(), '=') + "\n\n";
+  result += bins.to_string();
+  result += ScoreAsString(scores, square_scores, total_weight);
+  for (const Sensitivity& s : sensitivities)
+    result += s.name + "\n" + std::string(s.name.size(), '=') + "\n\n" + ScoreAsString(s.scores, s.square_scores, total_weight) + "\n";
+  return result;
 }
 
 Estimator& Estimator::operator+=(const Estimator& other) noexcept {
@@ -599,13 +644,28 @@ Estimator& Estimator::operator+=(const Estimator& other) noexcept {
     scores[i] += other.scores[i];
     square_scores[i] += other.square_scores[i];
   }
+  // Estimator.cpp:62-70: sensitivities are matched by name
+  for (Sensitivity& s : sensitivities) {
+    const auto matched = std::find_if(other.sensitivities.cbegin(), other.sensitivities.cend(), [&](const Sensitivity& o) { return o.name == s.name; });
+    if (matched == other.sensitivities.cend()) continue;
+    for (size_t i = 0; i < s.scores.size(); i++) {
+      s.scores[i] += matched->scores[i];
+      s.square_scores[i] += matched->square_scores[i];
+    }
+  }
   return *this;
 }
 
-EstimatorSet::EstimatorSet(const xml::Node* estimators_node, const World& world, Real total_weight)
+EstimatorSet::EstimatorSet(const xml::Node* estimators_node, const World& world, const PerturbationSet& perturbations, Real total_weight)
     : total_weight{total_weight} {
   if (estimators_node)
-    for (const auto& estimator_node : estimators_node->children()) estimators.emplace_back(*estimator_node, world);
+    for (const auto& estimator_node : estimators_node->children()) estimators.emplace_back(*estimator_node, world, perturbations);
+}
+
+size_t EstimatorSet::total_sensitivities() const noexcept {
+  size_t n = 0;
+  for (const auto& e : estimators) n += e.sensitivities.size();
+  return n;
 }
 
 const Estimator& EstimatorSet::FindEstimatorByName(const std::string& name) const {

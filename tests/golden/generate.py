@@ -33,10 +33,25 @@ def deck_text(name, tracking):
     return decks.DECKS[name](tracking=TRACKING[tracking], **kw)
 
 
+def sensitivity_fixtures(tmp, tables):
+    """sens/<deck>__<tracking>.out: decks with <perturbations> and <sensitivities> (Perturbation.cpp, Sensitivity.cpp)."""
+    (HERE / "sens").mkdir(exist_ok=True)
+    for name, tracking, text in util.sensitivity_cases(tables):
+        path = tmp / f"sens_{name}.xml"
+        path.write_text(text)
+        out, _ = port_py.ref_run(path)
+        (HERE / "sens" / f"{name}__{tracking}.out").write_text(out)
+
+
 def main():
     if not port_py.ref_available():
         raise SystemExit("oracle/_ref/ref_harness missing: run `make -C oracle ref` where /root/reference exists")
     tmp = Path(tempfile.mkdtemp())
+    if sys.argv[1:] == ["sens"]:  # only the sensitivity fixtures
+        from minimc_b200 import ce_decks
+        ce_decks.generate_tables(tmp / "tables", "small")
+        sensitivity_fixtures(tmp, tmp / "tables")
+        return
     for name in decks.DECKS:
         for tracking in TRACKING:
             path = tmp / f"{name}.xml"
@@ -62,6 +77,7 @@ def main():
         trace = subprocess.run([os.fspath(port_py.REF_HARNESS), "trace", os.fspath(path), "0", str(util.CE_TRACE_HISTORIES)],
                                capture_output=True, text=True, check=True).stdout
         (HERE / "ce" / f"{name}__{tracking}.trace").write_text(trace)
+    sensitivity_fixtures(tmp, tables)
     rng = {}
     for seed in (1, 0, 2147483647, 2147483648, 12345, 4294967297):
         lines = subprocess.run([os.fspath(port_py.REF_HARNESS), "rng", str(seed), "8"], capture_output=True, text=True,

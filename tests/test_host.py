@@ -187,3 +187,18 @@ def test_solve_without_gpu_fails_loudly():
     with pytest.raises(capi.MinimcError) as e:
         d.solve()
     assert "no CUDA device" in e.value.message
+
+
+def test_perturbations_and_sensitivities_parse_with_the_reference_messages():
+    """Perturbation.cpp:101-119, World.cpp:64-81: unknown perturbation / nuclide names are reported as the reference
+    reports them; a valid deck builds an EstimatorSet whose sensitivities are named estimator::perturbation."""
+    from minimc_b200 import decks
+    text = decks.sensitivity_shells(histories=100)
+    drv = capi.Driver(text=text)
+    assert drv.total_bins == 2 + 2 + 12
+    with pytest.raises(capi.MinimcError) as e:
+        capi.Driver(text=text.replace('<perturbation name="o-total"/>', '<perturbation name="nope"/>', 1))
+    assert 'Perturbation "nope" not found. Must be one of: ["h-total", "o-total", ]' in str(e.value)
+    with pytest.raises(capi.MinimcError) as e:
+        capi.Driver(text=text.replace('nuclide="oxygen"', 'nuclide="xenon"'))
+    assert 'Nuclide "xenon" not found. Must be one of: [' in str(e.value)

@@ -147,3 +147,22 @@ def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
 CE_CASE_IDS = [("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
                ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "surface"),
                ("free_gas_sphere", "delta")]
+
+
+# ---------------------------------------------------------------- sensitivities
+SENS_HISTORIES = 20000
+
+
+def sensitivity_cases(table_dir, histories=SENS_HISTORIES, seed=None):
+    """(deck name, tracking tag, XML text) of every differential-operator sensitivity parity case.  One reference
+    worker thread: the reference's real-valued sums then have one fixed order."""
+    from minimc_b200 import ce_decks
+    cases = []
+    for tag, tracking in TRACKING.items():
+        cases.append(("sensitivity_shells", tag, decks.sensitivity_shells(histories=histories, threads=1, seed=seed, tracking=tracking)))
+        cases.append(("sensitivity_slab", tag, ce_decks.sensitivity_slab_deck(table_dir, histories=histories // 5, threads=1,
+                                                                           seed=seed, tracking=tracking)))
+    return cases
+
+
+SENS_CASE_IDS = [(name, tag) for name in ("sensitivity_shells", "sensitivity_slab") for tag in TRACKING]
