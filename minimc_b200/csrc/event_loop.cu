@@ -74,6 +74,11 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_slots) {
     st.event[i] = MMC_EV_CAPTURE;  // "dead": the first pass refills every slot
+    // the flight kernel loads a slot's particle together with its event code, before it knows the slot is dead
+    st.px[i] = st.py[i] = st.pz[i] = st.dx[i] = st.dy[i] = st.dz[i] = st.energy[i] = st.tsl_T[i] = 0.0;
+    st.rng[i] = 0;
+    st.cell[i] = st.surface[i] = -1;
+    st.tsl_off[i] = 0;
     st.n_pending[i] = 0;
     st.dq_head[i] = 0;
     st.dq_count[i] = 0;
