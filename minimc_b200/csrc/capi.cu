@@ -643,6 +643,16 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
   h.off_cell_material = b.add(d->cell_material, d->n_cells);
   h.off_cell_surf_begin = b.add(d->cell_surface_begin, d->n_cells + 1);
   h.off_cell_surf = b.add(packed.data(), packed.size());
+  std::vector<SurfaceRecord> records(nnz_cell);
+  for (int k = 0; k < nnz_cell; k++) {
+    const int s_index = d->cell_surface_index[k];
+    SurfaceRecord& r = records[k];
+    r = SurfaceRecord{};
+    for (int j = 0; j < 4; j++) r.prm[j] = d->surface_param[4 * s_index + j];
+    r.type = d->surface_type[s_index];
+    r.index_sense = packed[k];
+  }
+  h.off_cell_surf_rec = b.add(records.data(), records.size());
   h.off_cell_field_kind = b.add(field_kind.data(), field_kind.size());
   h.off_cell_field_param = b.add(field_param.data(), field_param.size());
   const int32_t zero_begin[1] = {0};

@@ -203,16 +203,17 @@ __device__ __forceinline__ bool surface_contains(int32_t type, const double* prm
 // Returns -1 where the reference throws.
 __device__ inline int32_t find_cell(const WorldView& w, double px, double py, double pz) {
   const int32_t* begin = w.at<int32_t>(w.h->off_cell_surf_begin);
-  const int32_t* surf = w.at<int32_t>(w.h->off_cell_surf);
-  const int32_t* type = w.at<int32_t>(w.h->off_surface_type);
-  const double* prm = w.at<double>(w.h->off_surface_param);
+  const SurfaceRecord* rec = w.at<SurfaceRecord>(w.h->off_cell_surf_rec);
+  int32_t k = begin[0];
   for (int32_t c = 0; c < w.h->n_cells; c++) {
+    const int32_t end = begin[c + 1];
     bool inside = true;
-    for (int32_t k = begin[c]; k < begin[c + 1] && inside; k++) {
-      const int32_t s = surf[k] >> 1;
-      inside = surface_contains(type[s], prm + 4 * s, px, py, pz) == ((surf[k] & 1) != 0);
+    for (; k < end && inside; k++) {
+      const SurfaceRecord& r = rec[k];
+      inside = surface_contains(r.type, r.prm, px, py, pz) == ((r.index_sense & 1) != 0);
     }
     if (inside) return c;
+    k = end;
   }
   return -1;
 }
@@ -220,19 +221,15 @@ __device__ inline int32_t find_cell(const WorldView& w, double px, double py, do
 // Cell::NearestSurface, Cell.cpp:37-51: std::min_element keeps the FIRST minimum.
 __device__ __forceinline__ double nearest_surface(const WorldView& w, const Particle& p, int32_t& nearest) {
   const int32_t* begin = w.at<int32_t>(w.h->off_cell_surf_begin);
-  const int32_t* surf = w.at<int32_t>(w.h->off_cell_surf);
-  const int32_t* type = w.at<int32_t>(w.h->off_surface_type);
-  const double* prm = w.at<double>(w.h->off_surface_param);
+  const SurfaceRecord* rec = w.at<SurfaceRecord>(w.h->off_cell_surf_rec);
   const int32_t b = begin[p.cell], e = begin[p.cell + 1];
-  int32_t s = surf[b] >> 1;
-  double best = surface_distance(type[s], prm + 4 * s, p.px, p.py, p.pz, p.dx, p.dy, p.dz);
-  nearest = s;
+  double best = surface_distance(rec[b].type, rec[b].prm, p.px, p.py, p.pz, p.dx, p.dy, p.dz);
+  nearest = rec[b].index_sense >> 1;
   for (int32_t k = b + 1; k < e; k++) {
-    s = surf[k] >> 1;
-    const double d = surface_distance(type[s], prm + 4 * s, p.px, p.py, p.pz, p.dx, p.dy, p.dz);
+    const double d = surface_distance(rec[k].type, rec[k].prm, p.px, p.py, p.pz, p.dx, p.dy, p.dz);
     if (d < best) {
       best = d;
-      nearest = s;
+      nearest = rec[k].index_sense >> 1;
     }
   }
   return best;

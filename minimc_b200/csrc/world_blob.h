@@ -48,6 +48,15 @@ struct SourceSpec {
   double energy;
 };
 
+// One entry of a cell's surface list with the surface itself inline (48 bytes, 16-byte aligned): Cell::Contains and
+// Cell::NearestSurface walk a cell's entries with ONE load each instead of the index -> type -> parameters chain.
+struct SurfaceRecord {
+  double prm[4];         // CSGSurface parameters (sphere: centre + radius; planex: x; cylinderx: radius)
+  int32_t type;          // mmc_surface_type
+  int32_t index_sense;   // (surface index << 1) | sense
+  int32_t pad[2];
+};
+
 struct WorldHeader {
   uint32_t total_bytes;
   int32_t n_surfaces, n_cells, n_materials, n_nuclides, n_groups;
@@ -58,6 +67,7 @@ struct WorldHeader {
   uint32_t off_cell_material;   // int32[n_cells]
   uint32_t off_cell_surf_begin; // int32[n_cells+1]
   uint32_t off_cell_surf;       // int32[nnz]  (index << 1) | sense
+  uint32_t off_cell_surf_rec;   // SurfaceRecord[nnz]: the same list with each surface's type and parameters inline
   uint32_t off_cell_field_kind; // int32[n_cells]
   uint32_t off_cell_field_param;// double[n_cells][6]
   uint32_t off_mat_aden;        // double[n_materials]
