@@ -333,13 +333,16 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
 
 // ThermalScattering::Scatter (ThermalScattering.cpp:159-171) for the slots the flight kernel queued.
 //
-// ncu on B200 (profiles/r01d_*): this kernel is bound by L1 WAVEFRONTS -- every lane gathers its own 80-byte rows,
-// so one load instruction costs up to 32 cache-line lookups -- not by fp64 issue or HBM.  Hence one persistent CTA
-// per SM with the gathered tables in shared memory: (1) each lane's two mode rows in a [pair][thread] column
-// (ce::SharedRows: 4 conflict-free wavefronts per read instead of up to 32), (2) when it fits, the arena of every
-// partition's S*CDF_modes rows (WorldHeader::off_sc_arena, 44 KB at the reference's table shapes; rows are 80 bytes
-// apart, i.e. 5 sixteen-byte bank groups -- odd -- so rows that differ modulo 8 never conflict).
-// Warps walk the queue in chunks of 32 slots; state loads and stores are coalesced over the compacted queue.
+// ncu on B200 of the first version of this kernel (one thread per queue entry, every table read through L1): 88 % of
+// peak L1 WAVEFRONTS, 98 % L1 hit rate -- every lane gathers its own 80-byte rows, so one load instruction costs up
+// to 32 cache-line lookups.  The gather roof, not fp64 issue and not HBM.  Hence one persistent CTA per SM that keeps
+// what is gathered out of L1:
+//   (1) each lane's two mode rows in 40 registers (ce::RegisterRows, the default, 512 threads) or in a
+//       [pair][thread] column of shared memory (ce::SharedRows, 768 threads: 4 conflict-free wavefronts per read);
+//   (2) when it fits, the arena of every partition's S*CDF_modes rows in shared memory (WorldHeader::off_sc_arena,
+//       44 KB at the reference's table shapes; rows are 80 bytes apart, i.e. 5 sixteen-byte bank groups -- odd -- so
+//       rows that differ modulo 8 never conflict).
+// Warps claim chunks of 32 queue entries from a counter; state loads and stores are coalesced over the compacted queue.
 template <bool kSharedSc>
 __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ EventState st,
