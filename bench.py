@@ -85,7 +85,7 @@ def dram_traffic_per_step(workload, schedule, counters_per_rank):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -98,35 +98,50 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=fd, stderr=subprocess.DEVNULL)
             os.close(fd)
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
     def stop(self) -> dict:
+        """Median SM clock and throttle reasons of the samples taken between mark_begin() and mark_end() (the timed
+        region; nvidia-smi runs since before the warm-up, sampling every 50 ms).  A region shorter than the sampling
+        period is represented by the samples nearest to it."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # let a sample land after the region
         self.proc.terminate()
         self.proc.wait()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in Path(self.path).read_text().splitlines():
             f = [v.strip() for v in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.path)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        begin, end = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        inside = [r for r in rows if begin <= r[0] <= end]
+        if not inside and rows:  # shorter than the sampling period: the two samples that bracket the region
+            before = [r for r in rows if r[0] < begin][-1:]
+            after = [r for r in rows if r[0] > end][:1]
+            inside = before + after
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "samples": len(sm), "reasons": reasons}
 
 
 ROOFLINE_NOTE = {
@@ -256,16 +271,17 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
         if world_size > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few hundred ms before its first sample: it runs through the warm-up
     for _ in range(warmup):
         step()
     sync_all()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(steps)] for _ in range(4)]
     starts, ends, kernel_starts, kernel_ends = ev
     sync_all()
+    sampler.mark_begin()
     for k in range(steps):
         flush.fill_(k)  # evict L2 between timed iterations (untimed)
         starts[k].record(stream)
@@ -276,6 +292,7 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
         distributed.allreduce_sum_(scores, squares, counters)
         ends[k].record(stream)
     sync_all()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kernel_starts, kernel_ends))
