@@ -382,15 +382,20 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     if (i < n) {  // no early `continue`: every lane must come back to the shuffle above
     const uint32_t slot = q.tsl[i];
     Particle p;
-    p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
     p.energy = st.energy[slot];
     p.rng.x = st.rng[slot];
     const double T = st.tsl_T[slot];
     const TslTable& t = *w.at<TslTable>(st.tsl_off[slot]);
     bool error = false;
-    ce::tsl_scatter(w, t, p, T, error, rows);
-    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
-    st.energy[slot] = p.energy;
+    double mu = 0, E_p = 0;
+    ce::tsl_sample(w, t, p.rng, p.energy, T, error, rows, mu, E_p);
+    if (!error) {
+      // the direction is only needed now: it stays in memory while the sampler's state fills the registers
+      p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
+      ce::particle_scatter(p, mu, E_p);
+      st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
+      st.energy[slot] = p.energy;
+    }
     st.rng[slot] = p.rng.x;
     if (error) {
       // the reference throws here (-> std::terminate); the flight kernel counted the collision already
