@@ -308,11 +308,12 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool):
         drv.set_options(device=local_rank, profile=1)
         step()
         sync_all()
-        flight_ms, tsl_ms = drv.last_kernel_ms()
+        flight_ms, tsl_ms, boundary_ms = drv.last_kernel_ms()
         drv.set_options(device=local_rank)
         kernel_split = {"event_flight_kernel_ms": flight_ms, "event_tsl_kernel_ms": tsl_ms,
+                        "event_boundary_kernel_ms": boundary_ms,
                         "dominant": "event_tsl_kernel" if tsl_ms >= flight_ms else "event_flight_kernel",
-                        "dominant_share": max(flight_ms, tsl_ms) / max(flight_ms + tsl_ms, 1e-9),
+                        "dominant_share": max(flight_ms, tsl_ms) / max(flight_ms + tsl_ms + boundary_ms, 1e-9),
                         "launches": launches_per_step}
     c = dict(zip([n for n, _ in capi.Counters._fields_], counters.tolist()))
     assert c["n_histories"] == total_histories, (c["n_histories"], total_histories)

@@ -277,6 +277,7 @@ uint64_t mmc_world_last_launches(const mmc_world* world);
 /* With mmc_run_options.profile = 1: device time (ms, CUDA events on the run's stream) the last event-split run spent in
  * its flight kernels and in its S(a,b) kernels. */
 void mmc_world_last_kernel_ms(const mmc_world* world, double* flight_ms, double* tsl_ms);
+double mmc_world_last_boundary_ms(const mmc_world* world);  /* the boundary kernels (crossings, history ends, births) */
 
 /* Total number of bins of estimator e = cosine.n_bins * energy.n_bins
  * (ParticleBins::size, Bins.cpp:192-194). */
@@ -438,6 +439,7 @@ uint64_t mmc_driver_table_bytes(mmc_driver* driver);
 /* Kernels launched by the driver's last Solve() / run_device on this rank (mmc_world_last_launches). */
 uint64_t mmc_driver_last_launches(mmc_driver* driver);
 void mmc_driver_last_kernel_ms(mmc_driver* driver, double* flight_ms, double* tsl_ms);
+double mmc_driver_last_boundary_ms(mmc_driver* driver);
 /* Parity hook: mmc_trace_histories for histories [first, first + n) of a fixed-source deck. */
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records);

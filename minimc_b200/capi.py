@@ -109,7 +109,7 @@ EXPORTS = (
     "mmc_driver_set_shard", "mmc_driver_solve", "mmc_driver_batchsize", "mmc_driver_total_bins", "mmc_driver_scores",
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
     "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
-    "mmc_world_update", "mmc_driver_refresh_device", "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms",
+    "mmc_world_update", "mmc_driver_refresh_device", "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms", "mmc_world_last_boundary_ms", "mmc_driver_last_boundary_ms",
 )
 
 _lib = None
@@ -219,6 +219,9 @@ def load() -> C.CDLL:
     lib.mmc_world_update.argtypes = [C.c_void_p, C.c_void_p]
     for fn in (lib.mmc_world_last_launches, lib.mmc_driver_last_launches):
         fn.restype = C.c_uint64
+        fn.argtypes = [C.c_void_p]
+    for fn in (lib.mmc_world_last_boundary_ms, lib.mmc_driver_last_boundary_ms):
+        fn.restype = C.c_double
         fn.argtypes = [C.c_void_p]
     for fn in (lib.mmc_world_last_kernel_ms, lib.mmc_driver_last_kernel_ms):
         fn.restype = None
@@ -553,10 +556,10 @@ class Driver:
         return int(load().mmc_driver_last_launches(self._handle))
 
     def last_kernel_ms(self):
-        """(flight ms, S(a,b) ms) of the last event-split run made with set_options(profile=1)."""
+        """(flight ms, S(a,b) ms, boundary ms) of the last event-split run made with set_options(profile=1)."""
         a, b = C.c_double(), C.c_double()
         load().mmc_driver_last_kernel_ms(self._handle, C.byref(a), C.byref(b))
-        return a.value, b.value
+        return a.value, b.value, float(load().mmc_driver_last_boundary_ms(self._handle))
 
     def trace(self, first_history: int, n_histories: int, cap=1 << 18):
         records = (EventRecord * cap)()

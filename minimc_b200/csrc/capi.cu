@@ -148,7 +148,7 @@ struct mmc_world {
   size_t event_bytes = 0;
   unsigned int* h_event_counts = nullptr;
   uint64_t last_launches = 0;  // kernels launched by the last event-split run
-  double last_flight_ms = 0, last_tsl_ms = 0;  // profile mode: device time of the flight / S(a,b) kernels
+  double last_flight_ms = 0, last_tsl_ms = 0, last_boundary_ms = 0;  // profile mode: device time per kernel family
   // sensitivities: per-thread pending entries, device tallies with a pinned mirror
   SensitivityPending* d_sens_pending = nullptr;
   size_t sens_pending_bytes = 0;
@@ -462,7 +462,7 @@ struct EventBuffers {
 
 int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
   const size_t n = event_padded_slots(n_slots);  // keeps every array 128-byte aligned
-  const size_t need = n * (kEventStateBytesPerSlot + 3 * sizeof(uint32_t)) + 256 +
+  const size_t need = n * (kEventStateBytesPerSlot + 4 * sizeof(uint32_t)) + 256 +
                       kCounterReplicas * sizeof(mmc_counters);
   if (need > w->event_bytes) {
     scratch_release(w->device, kScratchEvent, w->d_event, w->event_bytes);
@@ -482,7 +482,7 @@ int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
   take(st.energy, n * 8), take(st.tsl_T, n * 8);
   take(st.rng, n * 4), take(st.cell, n * 4), take(st.surface, n * 4), take(st.event, n * 4);
   take(st.n_pending, n * 4), take(st.dq_head, n * 4), take(st.dq_count, n * 4), take(st.tsl_off, n * 4);
-  take(out.q.alive[0], n * 4), take(out.q.alive[1], n * 4), take(out.q.tsl, n * 4);
+  take(out.q.alive[0], n * 4), take(out.q.alive[1], n * 4), take(out.q.tsl, n * 4), take(out.q.boundary, n * 4);
   take(out.q.count, 256);
   take(out.counter_replicas, kCounterReplicas * sizeof(mmc_counters));
   return MMC_OK;
@@ -517,14 +517,16 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
   while (alive && status == MMC_OK) {
     const int batch = 8;
     for (int k = 0; k < batch && status == MMC_OK; k++, pass++) {
+      cudaEvent_t inner[2] = {nullptr, nullptr};
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
+      if (p.profile) inner[0] = mark(), inner[1] = mark();
       const cudaError_t err = launch_event_pass(
           w->d_blob, w->header, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
-          b.counter_replicas, tsl, p.stream, mark());
+          b.counter_replicas, tsl, p.stream, p.profile && inner[0] && inner[1] ? inner : nullptr);
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
       if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "launch_event_pass: %s", cudaGetErrorString(err));
     }
-    w->last_launches += 2 * batch;
+    w->last_launches += 3 * batch;
     cudaError_t err = cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream);
     if (err == cudaSuccess)
       err = cudaMemcpyAsync(w->h_event_counts + 4, w->d_next, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p.stream);
@@ -551,11 +553,12 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
       alive = 0;
     }
   }
-  w->last_flight_ms = w->last_tsl_ms = 0;
-  for (size_t k = 0; k + 2 < marks.size() + 0 && status == MMC_OK; k += 3) {
-    float a = 0, c = 0;
+  w->last_flight_ms = w->last_tsl_ms = w->last_boundary_ms = 0;
+  for (size_t k = 0; k + 3 < marks.size() && status == MMC_OK; k += 4) {  // before | after flight | after boundary | after S(a,b)
+    float a = 0, bd = 0, c = 0;
     if (cudaEventElapsedTime(&a, marks[k], marks[k + 1]) == cudaSuccess) w->last_flight_ms += a;
-    if (cudaEventElapsedTime(&c, marks[k + 1], marks[k + 2]) == cudaSuccess) w->last_tsl_ms += c;
+    if (cudaEventElapsedTime(&bd, marks[k + 1], marks[k + 2]) == cudaSuccess) w->last_boundary_ms += bd;
+    if (cudaEventElapsedTime(&c, marks[k + 2], marks[k + 3]) == cudaSuccess) w->last_tsl_ms += c;
   }
   for (cudaEvent_t e : marks) cudaEventDestroy(e);
   if (status != MMC_OK) return status;
@@ -611,6 +614,8 @@ void mmc_world_last_kernel_ms(const mmc_world* world, double* flight_ms, double*
   if (flight_ms) *flight_ms = world ? world->last_flight_ms : 0;
   if (tsl_ms) *tsl_ms = world ? world->last_tsl_ms : 0;
 }
+
+double mmc_world_last_boundary_ms(const mmc_world* world) { return world ? world->last_boundary_ms : 0; }
 
 uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
   if (!e) return 0;

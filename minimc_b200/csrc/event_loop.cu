@@ -24,11 +24,6 @@
 
 #include "kernel_common.cuh"
 
-// 1: the flight kernel's history claims, queue appends and counters are done per warp (no CTA barrier, 8x the
-// atomics); 0: per CTA through shared memory (four barriers).  Measured choice, see DESIGN.md s4.1.
-#ifndef MMC_EV_FLIGHT_WARP_LEVEL
-#define MMC_EV_FLIGHT_WARP_LEVEL 0
-#endif
 // flight kernel CTA: threads, and resident CTAs per SM the register allocation is tuned for (768 threads per SM)
 #ifndef MMC_EV_FLIGHT_THREADS
 #define MMC_EV_FLIGHT_THREADS 256
@@ -90,31 +85,90 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
   if (i < kCounterReplicas * kNumCounters) counter_replicas[i] = 0;
   if (i == 0) {
     q.count[0] = n_slots;
-    q.count[1] = q.count[2] = q.count[3] = q.count[4] = 0;
+    q.count[1] = q.count[2] = q.count[3] = q.count[4] = q.count[5] = q.count[6] = 0;
   }
 }
 
+// CTA-wide stream compaction of up to kQueues flags per thread: ballot + popc inside a warp, the warp totals scanned
+// in shared memory, ONE global atomic per CTA and queue, order inside the CTA preserved.  Returns each thread's
+// position in queue k (valid where its flag is set).
+template <int kQueues>
+struct CtaCompactor {
+  uint32_t totals[kQueues][kWarpsPerBlock];
+  uint32_t base[kQueues];
+};
+
+template <int kQueues>
+__device__ __forceinline__ void cta_compact(
+    CtaCompactor<kQueues>& sm, const bool (&flag)[kQueues], unsigned int* const (&counter)[kQueues], uint32_t (&position)[kQueues]) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  unsigned mask[kQueues];
+#pragma unroll
+  for (int k = 0; k < kQueues; k++) {
+    mask[k] = __ballot_sync(kFull, flag[k]);
+    if (lane == 0) sm.totals[k][warp] = __popc(mask[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < kQueues) {
+    uint32_t total = 0;
+    for (int wi = 0; wi < kWarpsPerBlock; wi++) total += sm.totals[threadIdx.x][wi];
+    sm.base[threadIdx.x] = total ? atomicAdd(counter[threadIdx.x], total) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kQueues; k++) {
+    uint32_t total;
+    position[k] = sm.base[k] + warp_prefix(sm.totals[k], warp, total) + __popc(mask[k] & lanes_below);
+  }
+}
+
+// per-CTA counter flush: the 0/1-per-lane counters packed four to a word, one warp reduction (REDUX) per word, the
+// warp sums through shared memory, one atomic per non-zero counter and CTA into one of 64 replicas
+__device__ __forceinline__ void flush_counters_cta(
+    const ThreadCounters& c, bool has_secondaries, uint4* s_packed, unsigned long long* counter_replicas) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t pa = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
+  const uint32_t pb = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
+  const uint32_t pd = c.scores | (c.capacity << 16);  // at most kMaxEstimators + 1 each per lane
+  const uint32_t sa = __reduce_add_sync(kFull, pa), sb = __reduce_add_sync(kFull, pb), sd = __reduce_add_sync(kFull, pd);
+  const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
+  if (lane == 0) s_packed[warp] = make_uint4(sa, sb, sd, ss);
+  __syncthreads();
+  if (threadIdx.x < kNumCounters) {
+    // mmc_counters order: histories, births, events, collisions, crossings, virtual, scores, secondaries, banked,
+    // lost, capacity, physics -> (word, shift, mask) of the packed sums
+    const uint32_t k = threadIdx.x;
+    const uint32_t word = (k == 2 || k == 3 || k == 4 || k == 5) ? 0u : (k == 0 || k == 1 || k == 9 || k == 11) ? 1u : (k == 6 || k == 10) ? 2u : 3u;
+    const uint32_t shift = k == 3 ? 8u : k == 4 ? 16u : k == 5 ? 24u : k == 1 ? 8u : k == 9 ? 16u : k == 11 ? 24u : k == 10 ? 16u : 0u;
+    const uint32_t mask = word < 2u ? 0xffu : word == 2u ? 0xffffu : 0xffffffffu;
+    uint32_t sum = 0;
+    if (k != 8) {
+      for (int wi = 0; wi < kWarpsPerBlock; wi++) {
+        const uint4 v = s_packed[wi];
+        const uint32_t field = word == 0u ? v.x : word == 1u ? v.y : word == 2u ? v.z : v.w;
+        sum += (field >> shift) & mask;
+      }
+    }
+    if (sum) atomicAdd(counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters + k, static_cast<unsigned long long>(sum));
+  }
+}
+
+// ---- flight: one Transport-loop iteration of every live particle up to the point where the event's kind is known
 template <int kTracking>
 __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_flight_kernel(
     const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
-    const double* __restrict__ bounds, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
-    uint32_t pass, BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
-    unsigned long long* scores, unsigned long long* square_scores, unsigned long long* counter_replicas) {
-#if !MMC_EV_FLIGHT_WARP_LEVEL
-  __shared__ uint32_t s_totals[3][kWarpsPerBlock];  // per-warp counts: history claims, live slots, S(a,b) slots
-  __shared__ unsigned long long s_claim_base;
-  __shared__ uint32_t s_queue_base[2];
-  __shared__ uint4 s_packed[kWarpsPerBlock];  // per-warp packed counter sums
-#endif
+    const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
+    BankSite* __restrict__ site_scratch, unsigned long long* counter_replicas) {
+  __shared__ CtaCompactor<3> s_compact;  // live slots, S(a,b) slots, boundary slots
+  __shared__ uint4 s_packed[kWarpsPerBlock];
 
   const uint32_t parity = pass & 1u;
   const uint32_t first = blockIdx.x * kFlightThreads;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t i = first + threadIdx.x;
   // Two dependent round trips to HBM instead of four: the queue entry is read together with the queue length (the
   // queues are zero-filled past their end, so a stale entry is a valid slot), and the whole particle together with
-  // the slot's event code (a dead slot's particle is loaded in vain: 4 % of the slots in a steady-state pass).
+  // the slot's event code (a dead slot's particle is loaded in vain).
   const uint32_t slot = q.alive[parity][i];
   const uint32_t n = q.count[parity];
   Particle p;
@@ -125,15 +179,106 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   p.group = 0;
   p.rng.x = st.rng[slot];
   p.cell = st.cell[slot];
-  p.surface = st.surface[slot];
+  p.surface = -1;  // written only by a crossing; tallies read it in the boundary kernel
   if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = 0;  // chunk counter of this pass's S(a,b) kernel
   if (first >= n) return;  // CTA-uniform
   const bool valid = i < n;
   const WorldView w(world_g, &header);
   const bool has_secondaries = run.secondary_capacity > 1;
 
-  if (!valid) p.event = MMC_EV_CAPTURE;
-  bool alive = valid && is_alive(p.event);
+  const bool retired = !valid || p.event == kEvRetired;
+  const bool alive = !retired && is_alive(p.event);
+  SiteDeque dq;
+  dq.slots = site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
+  dq.mask = run.secondary_capacity - 1;
+  dq.head = 0;
+  dq.count = 0;
+  if (alive && has_secondaries) {
+    dq.head = st.dq_head[slot];
+    dq.count = st.dq_count[slot];
+  }
+  ThreadCounters c;
+  StepOut o;
+  o.secondaries = 0;
+  o.need_direction = false;
+  o.need_tsl = o.need_cross = false;
+  o.error_physics = o.error_capacity = o.error_lost = false;
+  if (alive) {
+    // p.cell >= 0: the boundary kernel looked the Cell up at birth and after every crossing
+    transport_step<kTracking, true, false, true, false, true>(w, p, dq, o);
+    count_event(c, p, o);
+    st.px[slot] = p.px, st.py[slot] = p.py, st.pz[slot] = p.pz;
+    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
+    st.energy[slot] = p.energy;
+    st.rng[slot] = p.rng.x;
+    st.event[slot] = p.event;
+    if (o.need_cross) st.surface[slot] = p.surface;
+    if (has_secondaries) {
+      st.dq_head[slot] = dq.head;
+      st.dq_count[slot] = dq.count;
+    }
+    if (o.need_tsl) {
+      st.tsl_T[slot] = o.tsl_T;
+      st.tsl_off[slot] = o.tsl_off;
+    }
+  }
+  // ---- stream compaction into the three queues of this pass
+  //   live:     every slot that has not retired (it is looked at again next pass)
+  //   S(a,b):   the collision chose thermal scattering
+  //   boundary: the particle is on a surface (Cell lookup, leak, tallies), or the slot's particle is dead (capture,
+  //             leak, fission; a dead slot of the previous pass, e.g. all of them in pass 0): next particle / history
+  const bool flag[3] = {!retired, alive && o.need_tsl, !retired && (o.need_cross || !is_alive(p.event))};
+  unsigned int* const counter[3] = {&q.count[parity ^ 1u], &q.count[2u + parity], &q.count[5u + parity]};
+  uint32_t position[3];
+  cta_compact<3>(s_compact, flag, counter, position);
+  if (flag[0]) q.alive[parity ^ 1u][position[0]] = slot;
+  if (flag[1]) q.tsl[position[1]] = slot;
+  if (flag[2]) q.boundary[position[2]] = slot;
+  flush_counters_cta(c, has_secondaries, s_packed, counter_replicas);
+}
+
+// ---- boundary: the rare ends of an event, run densely over the slots the flight kernel queued.
+//   * a particle on a surface: World::FindCellContaining, surface_cross or leak (TransportMethod.cpp:68-73),
+//     EstimatorSetProxy::Score (:74) -- `current` estimators score nothing else;
+//   * a dead particle (captured or fissioned in this pass's flight, leaked just above, or dead since an earlier
+//     pass): the next particle of the slot's history from its bank (FixedSource.cpp:63-71), else a new history
+//     (one atomic per CTA claims the indices), Source::Sample, and the Cell of the newborn (TransportMethod.cpp:55);
+//     a slot that finds no history left retires.
+// In a steady-state single_zone pass 8 % of the live slots come here (4 % crossings, 4 % history ends); inside the
+// flight kernel these branches ran with one or two lanes of a warp while the others waited.
+template <int kTracking>
+__global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
+    const double* __restrict__ bounds, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
+    uint32_t pass, BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch,
+    unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
+    unsigned long long* counter_replicas) {
+  __shared__ uint32_t s_claims[kWarpsPerBlock];
+  __shared__ unsigned long long s_claim_base;
+  __shared__ uint4 s_packed[kWarpsPerBlock];
+
+  const uint32_t parity = pass & 1u;
+  const uint32_t n = q.count[5u + parity];
+  const uint32_t first = blockIdx.x * kFlightThreads;
+  if (first >= n) return;  // CTA-uniform
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t i = first + threadIdx.x;
+  const bool valid = i < n;
+  const uint32_t slot = valid ? q.boundary[i] : 0u;
+  const WorldView w(world_g, &header);
+  const bool has_secondaries = run.secondary_capacity > 1;
+
+  Particle p;
+  p.event = valid ? st.event[slot] : kEvRetired;
+  p.px = st.px[slot], p.py = st.py[slot], p.pz = st.pz[slot];
+  p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
+  p.energy = st.energy[slot];
+  p.group = 0;
+  p.rng.x = st.rng[slot];
+  p.cell = st.cell[slot];
+  p.surface = st.surface[slot];
+  uint32_t n_pending = run.n_estimators ? st.n_pending[slot] : 0u;
   SiteDeque dq;
   dq.slots = site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
   dq.mask = run.secondary_capacity - 1;
@@ -143,88 +288,26 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
     dq.head = st.dq_head[slot];
     dq.count = st.dq_count[slot];
   }
-  uint32_t n_pending = (valid && run.n_estimators) ? st.n_pending[slot] : 0u;
   ThreadCounters c;
 
-  // ---- refill: next particle of the slot's history (bank.back(), FixedSource.cpp:63-71) ...
-  if (valid && !alive && dq.count) {
-    dq.count--;
-    load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
-    alive = true;
-    c.births++;
+  // ---- the second half of a crossing, and its tallies
+  const bool crossing = p.event == kEvCrossPending;
+  bool lost = false;
+  if (crossing) {
+    StepOut o;
+    o.error_lost = false;
+    finish_crossing(w, p, o);
+    lost = o.error_lost;
+    c.crossings++;  // count_event: surface_cross or leak (a lost particle is recorded as a leak)
+    c.lost += lost;
   }
-  // ... else a new history: one atomic per CTA claims the indices
-  const bool need = valid && !alive;
-  const unsigned need_mask = __ballot_sync(kFull, need);
-#if MMC_EV_FLIGHT_WARP_LEVEL
-  unsigned long long claim_base = 0;
-  if (need_mask) {
-    if (lane == 0) {
-      claim_base = *reinterpret_cast<volatile unsigned long long*>(next_history);
-      if (claim_base < run.n_histories) claim_base = atomicAdd(next_history, static_cast<unsigned long long>(__popc(need_mask)));
-    }
-    claim_base = __shfl_sync(kFull, claim_base, 0);
-  }
-  const uint32_t claim_prefix = 0;
-#else
-  if (lane == 0) s_totals[0][warp] = __popc(need_mask);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t total = 0;
-    for (int k = 0; k < kWarpsPerBlock; k++) total += s_totals[0][k];
-    unsigned long long base = 0;
-    if (total) {
-      base = *reinterpret_cast<volatile unsigned long long*>(next_history);
-      if (base < run.n_histories) base = atomicAdd(next_history, static_cast<unsigned long long>(total));
-    }
-    s_claim_base = base;
-  }
-  __syncthreads();
-  uint32_t claim_total;
-  const unsigned long long claim_base = s_claim_base;
-  const uint32_t claim_prefix = warp_prefix(s_totals[0], warp, claim_total);
-#endif
-  bool retired = false;
-  if (need) {
-    const uint64_t idx = claim_base + claim_prefix + __popc(need_mask & lanes_below);
-    if (idx < run.n_histories) {
-      // a new scoring proxy starts empty: FixedSource.cpp:48
-      n_pending = 0;
-      sample_source(run.source, run.seed0 + run.first_history + idx, p);
-      alive = true;
-      c.histories++;
-      c.births++;
-    } else {
-      retired = true;  // no work left for this slot
-    }
-  }
-
-  // ---- one event
-  StepOut o;
-  o.secondaries = 0;
-  o.need_direction = false;
-  o.need_tsl = false;
-  o.error_physics = o.error_capacity = o.error_lost = false;
-  if (alive) {
-    if (p.cell < 0) {
-      // TransportMethod.cpp:55: p.SetCell(w.FindCellContaining(p.GetPosition()))
-      p.cell = find_cell(w, p.px, p.py, p.pz);
-      if (p.cell < 0) {
-        o.error_lost = true;
-        p.event = MMC_EV_LEAK;
-      }
-    }
-    if (p.cell >= 0) transport_step<kTracking, true, false, true>(w, p, dq, o);
-    count_event(c, p, o);
-  }
-
-  // ---- EstimatorSetProxy::Score(p): TransportMethod.cpp:74 (see kernels.cu for the incremental commit)
   uint2* pending = pending_scratch + static_cast<size_t>(slot) * run.pending_capacity;
   for (int32_t e = 0; e < run.n_estimators; e++) {
     uint64_t bin = 0;
-    const bool hit = alive && !o.error_lost && estimator_score<true>(run.estimators[e], bounds, p, bin);
+    const bool hit = crossing && !lost && estimator_score<true>(run.estimators[e], bounds, p, bin);
     const unsigned hit_mask = __ballot_sync(kFull, hit);
     if (hit) {
+      // incremental CommitHistory: the k-th hit of a history in a bin adds 1 and 2k - 1 (see kernels.cu)
       uint32_t k = 0, s = 0;
       for (; s < n_pending; s++)
         if (pending[s].x == static_cast<uint32_t>(bin)) break;
@@ -246,8 +329,55 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
     }
   }
 
-  // ---- state back to HBM
-  if (alive) {
+  // ---- a dead particle: the next one of the history's bank, else a new history
+  bool alive = valid && is_alive(p.event);
+  bool born = false;
+  if (valid && !alive && dq.count) {
+    dq.count--;
+    load_site(dq.slots[(dq.head + dq.count) & dq.mask], p);
+    alive = born = true;
+    c.births++;
+  }
+  const bool need = valid && !alive;
+  const unsigned need_mask = __ballot_sync(kFull, need);
+  if (lane == 0) s_claims[warp] = __popc(need_mask);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int k = 0; k < kWarpsPerBlock; k++) total += s_claims[k];
+    unsigned long long base = 0;
+    if (total) {
+      base = *reinterpret_cast<volatile unsigned long long*>(next_history);
+      if (base < run.n_histories) base = atomicAdd(next_history, static_cast<unsigned long long>(total));
+    }
+    s_claim_base = base;
+  }
+  __syncthreads();
+  if (need) {
+    uint32_t total;
+    const uint64_t idx = s_claim_base + warp_prefix(s_claims, warp, total) + __popc(need_mask & lanes_below);
+    if (idx < run.n_histories) {
+      n_pending = 0;  // a new scoring proxy starts empty: FixedSource.cpp:48
+      sample_source(run.source, run.seed0 + run.first_history + idx, p);
+      alive = born = true;
+      c.histories++;
+      c.births++;
+    } else {
+      p.event = kEvRetired;  // no work left for this slot
+    }
+  }
+  if (born) {
+    // TransportMethod.cpp:55: p.SetCell(w.FindCellContaining(p.GetPosition())); a newborn outside every Cell is what
+    // the fused kernel records as one lost event (a leak)
+    p.cell = find_cell(w, p.px, p.py, p.pz);
+    if (p.cell < 0) {
+      p.event = MMC_EV_LEAK;
+      c.events++;
+      c.crossings++;
+      c.lost++;
+    }
+  }
+  if (valid) {
     st.px[slot] = p.px, st.py[slot] = p.py, st.pz[slot] = p.pz;
     st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
     st.energy[slot] = p.energy;
@@ -260,75 +390,8 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
       st.dq_head[slot] = dq.head;
       st.dq_count[slot] = dq.count;
     }
-    if (o.need_tsl) {
-      st.tsl_T[slot] = o.tsl_T;
-      st.tsl_off[slot] = o.tsl_off;
-    }
   }
-
-  // ---- stream compaction: slots that still have work, and slots awaiting S(a,b) sampling
-  const bool keep = valid && !retired;
-  const bool to_tsl = alive && o.need_tsl;
-  const unsigned keep_mask = __ballot_sync(kFull, keep);
-  const unsigned tsl_mask = __ballot_sync(kFull, to_tsl);
-  // ---- counters: the 0/1-per-lane counters packed four to a word, one warp reduction per word
-  const uint32_t pa = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
-  const uint32_t pb = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
-  const uint32_t pd = c.scores | (c.capacity << 16);  // at most kMaxEstimators + 1 each per lane
-  const uint32_t sa = __reduce_add_sync(kFull, pa), sb = __reduce_add_sync(kFull, pb), sd = __reduce_add_sync(kFull, pd);
-  const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
-#if MMC_EV_FLIGHT_WARP_LEVEL
-  // no CTA barrier anywhere: every warp appends to the queues and adds its counters on its own
-  uint32_t keep_base = 0, tsl_base = 0;
-  if (lane == 0) {
-    if (keep_mask) keep_base = atomicAdd(&q.count[parity ^ 1u], static_cast<unsigned int>(__popc(keep_mask)));
-    if (tsl_mask) tsl_base = atomicAdd(&q.count[2u + parity], static_cast<unsigned int>(__popc(tsl_mask)));
-    unsigned long long* mine = counter_replicas + ((blockIdx.x * kWarpsPerBlock + warp) % kCounterReplicas) * kNumCounters;
-    const uint32_t sums[kNumCounters] = {sb & 0xffu, (sb >> 8) & 0xffu, sa & 0xffu, (sa >> 8) & 0xffu, (sa >> 16) & 0xffu, sa >> 24,
-                                         sd & 0xffffu, ss, 0u, (sb >> 16) & 0xffu, sd >> 16, sb >> 24};
-#pragma unroll
-    for (int k = 0; k < kNumCounters; k++)
-      if (sums[k]) atomicAdd(mine + k, static_cast<unsigned long long>(sums[k]));
-  }
-  keep_base = __shfl_sync(kFull, keep_base, 0);
-  tsl_base = __shfl_sync(kFull, tsl_base, 0);
-  if (keep) q.alive[parity ^ 1u][keep_base + __popc(keep_mask & lanes_below)] = slot;
-  if (to_tsl) q.tsl[tsl_base + __popc(tsl_mask & lanes_below)] = slot;
-#else
-  if (lane == 0) {
-    s_totals[1][warp] = __popc(keep_mask);
-    s_totals[2][warp] = __popc(tsl_mask);
-    s_packed[warp] = make_uint4(sa, sb, sd, ss);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t keep_total = 0, tsl_total = 0;
-    for (int k = 0; k < kWarpsPerBlock; k++) keep_total += s_totals[1][k], tsl_total += s_totals[2][k];
-    s_queue_base[0] = keep_total ? atomicAdd(&q.count[parity ^ 1u], keep_total) : 0u;
-    s_queue_base[1] = tsl_total ? atomicAdd(&q.count[2u + parity], tsl_total) : 0u;
-  }
-  if (threadIdx.x < kNumCounters) {
-    // mmc_counters order: histories, births, events, collisions, crossings, virtual, scores, secondaries, banked,
-    // lost, capacity, physics -> (word, shift, mask) of the packed sums
-    const uint32_t k = threadIdx.x;
-    const uint32_t word = (k == 2 || k == 3 || k == 4 || k == 5) ? 0u : (k == 0 || k == 1 || k == 9 || k == 11) ? 1u : (k == 6 || k == 10) ? 2u : 3u;
-    const uint32_t shift = k == 3 ? 8u : k == 4 ? 16u : k == 5 ? 24u : k == 1 ? 8u : k == 9 ? 16u : k == 11 ? 24u : k == 10 ? 16u : 0u;
-    const uint32_t mask = word < 2u ? 0xffu : word == 2u ? 0xffffu : 0xffffffffu;
-    uint32_t sum = 0;
-    if (k != 8) {
-      for (int wi = 0; wi < kWarpsPerBlock; wi++) {
-        const uint4 v = s_packed[wi];
-        const uint32_t field = word == 0u ? v.x : word == 1u ? v.y : word == 2u ? v.z : v.w;
-        sum += (field >> shift) & mask;
-      }
-    }
-    if (sum) atomicAdd(counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters + k, static_cast<unsigned long long>(sum));
-  }
-  __syncthreads();
-  uint32_t total;
-  if (keep) q.alive[parity ^ 1u][s_queue_base[0] + warp_prefix(s_totals[1], warp, total) + __popc(keep_mask & lanes_below)] = slot;
-  if (to_tsl) q.tsl[s_queue_base[1] + warp_prefix(s_totals[2], warp, total) + __popc(tsl_mask & lanes_below)] = slot;
-#endif
+  flush_counters_cta(c, has_secondaries, s_packed, counter_replicas);
 }
 
 // ThermalScattering::Scatter (ThermalScattering.cpp:159-171) for the slots the flight kernel queued.
@@ -354,6 +417,7 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     q.count[parity] = 0;             // the alive queue this pass consumed: the next pass appends to it
     q.count[2u + (parity ^ 1u)] = 0; // the S(a,b) queue of the next pass
+    q.count[5u + (parity ^ 1u)] = 0; // the boundary queue of the next pass
   }
   const uint32_t n = q.count[2u + parity];
   constexpr uint32_t kWarps = kTslThreads / 32;
@@ -432,18 +496,25 @@ cudaError_t launch_event_pass(
     const char* world_d, const WorldHeader& header, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
-    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream, cudaEvent_t after_flight) {
+    unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream, const cudaEvent_t* marks) {
   const uint32_t blocks = (alive_upper_bound + kFlightThreads - 1) / kFlightThreads;
   if (blocks == 0) return cudaSuccess;
   if (run.tracking == MMC_TRACK_CELL_DELTA)
     event_flight_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kFlightThreads, 0, stream>>>(
+        world_d, header, run, st, q, pass, site_scratch, counter_replicas);
+  else
+    event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
+        world_d, header, run, st, q, pass, site_scratch, counter_replicas);
+  if (marks) cudaEventRecord(marks[0], stream);
+  if (run.tracking == MMC_TRACK_CELL_DELTA)
+    event_boundary_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kFlightThreads, 0, stream>>>(
         world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
   else
-    event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
+    event_boundary_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
         world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
         counter_replicas);
-  if (after_flight) cudaEventRecord(after_flight, stream);
+  if (marks) cudaEventRecord(marks[1], stream);
   // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queue can feed
   const uint32_t per_cta = kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
   if (adopt) {
     const EventState& st = resume.st;
     p.event = st.event[scratch];
+    if (p.event == kEvRetired) p.event = MMC_EV_CAPTURE;  // a slot that already found no history left: dead
     p.px = st.px[scratch], p.py = st.py[scratch], p.pz = st.pz[scratch];
     p.dx = st.dx[scratch], p.dy = st.dy[scratch], p.dz = st.dz[scratch];
     p.energy = st.energy[scratch];
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
     o.secondaries = 0;
     o.need_direction = false;
     o.error_physics = o.error_capacity = o.error_lost = false;
-    o.need_tsl = false;
+    o.need_tsl = o.need_cross = false;
     if (alive) {
       if (p.cell < 0) {
         // TransportMethod.cpp:55: p.SetCell(w.FindCellContaining(p.GetPosition()))

@@ -83,7 +83,8 @@ struct ResumeIO {
 struct EventQueues {
   uint32_t* alive[2];   // compacted slot indices, ping-pong between passes
   uint32_t* tsl;        // slots whose collision awaits S(a,b) sampling in this pass
-  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity), [4] chunk counter of the S(a,b) kernel
+  uint32_t* boundary;   // slots whose particle is on a surface or dead: Cell lookup, tallies, next particle / history
+  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity), [4] chunk counter of the S(a,b) kernel, [5..6] boundary counts
 };
 
 constexpr int kCounterReplicas = 64;
@@ -99,13 +100,14 @@ struct EventTslConfig {
 
 cudaError_t launch_event_init(const EventState& st, const EventQueues& q, uint32_t n_slots,
                               unsigned long long* counter_replicas, cudaStream_t stream);
-// one pass = one event of every live slot: the flight kernel, then the S(a,b) kernel over the slots it queued
+// one pass = one event of every live slot: the flight kernel, then the boundary kernel and the S(a,b) kernel over the
+// slots it queued
 cudaError_t launch_event_pass(
     const char* world_d, const WorldHeader& header, const RunSpec& run, const double* bounds_d, const EventState& st, const EventQueues& q,
     uint32_t pass, uint32_t alive_upper_bound, BankSite* site_scratch, uint2* pending_scratch,
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
     unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream,
-    cudaEvent_t after_flight = nullptr);
+    const cudaEvent_t* marks = nullptr);  // profile mode: marks[0] after the flight kernel, marks[1] after the boundary kernel
 // shared-memory plan of the S(a,b) kernel for a world (opts the kernels into their dynamic shared memory)
 cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out);
 cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream);

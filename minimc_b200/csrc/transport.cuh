@@ -304,7 +304,14 @@ struct StepOut {
   bool need_tsl;
   uint32_t tsl_off;
   double tsl_T;
+  // event-split schedule: the particle streamed onto a surface and left Cell lookup, event code and tallies to the
+  // boundary kernel (p.event == kEvCrossPending meanwhile)
+  bool need_cross;
 };
+
+// event codes used only between the kernels of one event-split pass (never in records or counters)
+constexpr int32_t kEvCrossPending = 64;  // streamed to a surface: World::FindCellContaining still to do
+constexpr int32_t kEvRetired = 65;       // the slot found no history left: it leaves the live queue
 
 // Material::GetMicroscopicTotal (Material.cpp:53-62): accumulate afrac*total
 // from 0 in afracs order.  For multigroup GetMajorant == GetTotal
@@ -467,12 +474,25 @@ __device__ __forceinline__ void perturb_stream(const WorldView& w, const Perturb
 // One iteration of SurfaceTracking::Transport (TransportMethod.cpp:56-75) or
 // CellDeltaTracking::Transport (TransportMethod.cpp:92-120).  kCE selects the
 // Continuous (true) or Multigroup (false) Interaction of the world's nuclides.
-template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false, bool kPerturb = false>
+// the second half of a surface crossing (TransportMethod.cpp:68-73,100-105): the new Cell, leak or crossing
+__device__ __forceinline__ void finish_crossing(const WorldView& w, Particle& p, StepOut& out) {
+  p.cell = find_cell(w, p.px, p.py, p.pz);
+  if (p.cell < 0) {
+    out.error_lost = true;
+    p.event = MMC_EV_LEAK;
+    return;
+  }
+  p.event = w.at<int32_t>(w.h->off_cell_material)[p.cell] >= 0 ? MMC_EV_SURFACE_CROSS : MMC_EV_LEAK;
+}
+
+template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false, bool kPerturb = false,
+          bool kDeferCross = false>
 __device__ __forceinline__ void transport_step(
     const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out, const PerturbContext* pc = nullptr) {
   out.secondaries = 0;
   out.need_direction = false;
   out.need_tsl = false;
+  out.need_cross = false;
   out.error_physics = out.error_capacity = out.error_lost = false;
   const int32_t mat = w.at<int32_t>(w.h->off_cell_material)[p.cell];
   if (mat < 0) {  // born in a void cell: the reference dereferences a null Material
@@ -511,14 +531,13 @@ __device__ __forceinline__ void transport_step(
   if (cross) {
     if (kPerturb) perturb_stream(w, *pc, mat, majorant, __dadd_rn(d_surf, 2.220446049250313e-15));
     stream(p, __dadd_rn(d_surf, 2.220446049250313e-15));  // constants::nudge = 10 * epsilon
-    p.cell = find_cell(w, p.px, p.py, p.pz);
     p.surface = nearest;
-    if (p.cell < 0) {
-      out.error_lost = true;
-      p.event = MMC_EV_LEAK;
+    if (kDeferCross) {
+      out.need_cross = true;
+      p.event = kEvCrossPending;
       return;
     }
-    p.event = w.at<int32_t>(w.h->off_cell_material)[p.cell] >= 0 ? MMC_EV_SURFACE_CROSS : MMC_EV_LEAK;
+    finish_crossing(w, p, out);
   } else {
     bool real = true;
     if (kTracking == MMC_TRACK_CELL_DELTA) {

@@ -200,6 +200,16 @@ void mmc_driver_last_kernel_ms(mmc_driver* driver, double* flight_ms, double* ts
   }
 }
 
+double mmc_driver_last_boundary_ms(mmc_driver* driver) {
+  if (!driver) return 0;
+  try {
+    return mmc_world_last_boundary_ms(driver->driver->device_world_handle());
+  } catch (const std::exception& e) {
+    mmc::set_last_error(MMC_ERR_INVALID, e.what());
+    return 0;
+  }
+}
+
 int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_histories, mmc_event_record* records,
                      size_t cap, size_t* n_records) {
   return Guard([&] {
