@@ -3,19 +3,21 @@
 // The fused kernel (kernels.cu) keeps a particle in registers for its whole life.
 // For the S(a,b) decks that puts ~14 k instructions (230 KB) of divergent code in
 // one kernel: ncu shows warps waiting on instruction fetch as often as on memory.
-// Here one PASS advances every live history by one event with two small kernels:
+// Here one PASS advances every live history by one event with three small kernels:
 //
-//   event_flight_kernel   refill (next secondary / next history, Source::Sample), cross-section lookup,
-//                         distance to collision and to the nearest surface, crossing or collision, reaction
-//                         choice, tallies.  A collision that chose thermal scattering is not sampled here:
-//                         its slot goes to the S(a,b) queue.
-//   event_tsl_kernel      ThermalScattering::Scatter (SampleBeta, SampleAlpha, Particle::Scatter) for the
-//                         queued slots -- every lane of every warp runs the POD sampler.
+//   event_flight_kernel    cross-section lookup, distance to collision and to the nearest surface, the flight;
+//                          at a collision: nuclide and reaction choice, capture / free-gas scatter / fission.
+//                          A collision that chose thermal scattering is not sampled here (-> S(a,b) queue); a
+//                          particle that reached a surface, or died, is not finished here (-> boundary queue).
+//   event_boundary_kernel  dense over the boundary queue: Cell lookup after a crossing, leak, tallies; next
+//                          particle of the history's bank, next history (Source::Sample), retirement of the slot.
+//   event_tsl_kernel       ThermalScattering::Scatter (SampleBeta, SampleAlpha, Particle::Scatter) for the
+//                          S(a,b) queue -- every lane of every warp runs the POD sampler.
 //
 // Particle state streams through HBM as structure-of-arrays (EventState, kernels.h) indexed by SLOT; a slot is one
 // history context (current particle, pending-score table, secondary deque), so the per-history bookkeeping of
-// FixedSource.cpp:48-72 stays slot-local exactly as it is lane-local in the fused kernel.  Between kernels the live
-// slots and the S(a,b) slots are stream-compacted: ballot + popc inside a warp, the eight warp totals scanned in
+// FixedSource.cpp:48-72 stays slot-local exactly as it is lane-local in the fused kernel.  Between kernels the live,
+// S(a,b) and boundary slots are stream-compacted: ballot + popc inside a warp, the eight warp totals scanned in
 // shared memory, ONE global atomic per CTA and queue, order inside a CTA preserved.  The arithmetic per particle is
 // the same device code (transport.cuh, physics_ce.cuh) in the same order, so results stay bit-identical to the
 // fused kernel and to the reference; tallies are integer sums and do not depend on the schedule.
