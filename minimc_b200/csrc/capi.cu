@@ -658,6 +658,25 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
     r.index_sense = packed[k];
   }
   h.off_cell_surf_rec = b.add(records.data(), records.size());
+  if (d->n_surfaces <= 64) {
+    // Cell::Contains as one mask compare (Cell.cpp:27-35: every surface of the cell must have Contains(p) == sense)
+    std::vector<uint64_t> masks(static_cast<size_t>(d->n_cells) * 2, 0);
+    for (int c = 0; c < d->n_cells; c++) {
+      uint64_t mask = 0, want = 0;
+      bool contradictory = false;
+      for (int k = d->cell_surface_begin[c]; k < d->cell_surface_begin[c + 1]; k++) {
+        const uint64_t bit = 1ull << d->cell_surface_index[k];
+        const uint64_t sense = d->cell_surface_sense[k] ? bit : 0;
+        if ((mask & bit) && (want & bit) != sense) contradictory = true;  // the same surface with both senses
+        mask |= bit;
+        want |= sense;
+      }
+      if (contradictory) mask = 0, want = ~0ull;  // never equal: such a cell contains nothing
+      masks[2 * c] = mask;
+      masks[2 * c + 1] = want;
+    }
+    h.off_cell_mask = b.add(masks.data(), masks.size());
+  }
   h.off_cell_field_kind = b.add(field_kind.data(), field_kind.size());
   h.off_cell_field_param = b.add(field_param.data(), field_param.size());
   const int32_t zero_begin[1] = {0};

@@ -202,6 +202,21 @@ __device__ __forceinline__ bool surface_contains(int32_t type, const double* prm
 // every surface satisfies Contains(p) == sense (Cell::Contains, Cell.cpp:27-35).
 // Returns -1 where the reference throws.
 __device__ inline int32_t find_cell(const WorldView& w, double px, double py, double pz) {
+  if (w.h->off_cell_mask) {
+    // Contains() of every surface once (independent loads, no early exit: the lanes of a warp stay together), then
+    // each Cell is one mask compare; the first match in XML order, as the reference's scan
+    const int32_t* type = w.at<int32_t>(w.h->off_surface_type);
+    const double* prm = w.at<double>(w.h->off_surface_param);
+    unsigned long long inside = 0;
+    for (int32_t s = 0; s < w.h->n_surfaces; s++)
+      inside |= static_cast<unsigned long long>(surface_contains(type[s], prm + 4 * s, px, py, pz)) << s;
+    const ulonglong2* masks = w.at<ulonglong2>(w.h->off_cell_mask);
+    for (int32_t c = 0; c < w.h->n_cells; c++) {
+      const ulonglong2 m = masks[c];  // {mask, want}
+      if ((inside & m.x) == m.y) return c;
+    }
+    return -1;
+  }
   const int32_t* begin = w.at<int32_t>(w.h->off_cell_surf_begin);
   const SurfaceRecord* rec = w.at<SurfaceRecord>(w.h->off_cell_surf_rec);
   int32_t k = begin[0];

@@ -68,6 +68,8 @@ struct WorldHeader {
   uint32_t off_cell_surf_begin; // int32[n_cells+1]
   uint32_t off_cell_surf;       // int32[nnz]  (index << 1) | sense
   uint32_t off_cell_surf_rec;   // SurfaceRecord[nnz]: the same list with each surface's type and parameters inline
+  uint32_t off_cell_mask;       // uint64[n_cells][2] {mask, want}: Cell::Contains(p) <=> (inside(p) & mask) == want, where
+                                // bit s of inside(p) is surfaces[s].Contains(p); 0 when the world has more than 64 surfaces
   uint32_t off_cell_field_kind; // int32[n_cells]
   uint32_t off_cell_field_param;// double[n_cells][6]
   uint32_t off_mat_aden;        // double[n_materials]

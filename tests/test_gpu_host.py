@@ -126,3 +126,43 @@ def test_world_update_rejects_a_different_shape():
     other_desc, same_desc = other.desc(), same.desc()
     assert capi.load().mmc_world_update(world._handle, C.byref(other_desc)) == capi.ERR_INVALID
     assert capi.load().mmc_world_update(world._handle, C.byref(same_desc)) == 0
+
+
+@pytest.mark.parametrize("n_planes", [9, 64, 65, 90])
+def test_cell_lookup_in_a_stack_of_slabs(n_planes):
+    """World::FindCellContaining (World.cpp:26-37) over a stack of slabs between n planes: worlds of up to 64
+    surfaces evaluate every surface once and compare one mask per Cell, larger worlds walk each Cell's surface list;
+    both must give the first Cell in creation order that contains the point.  A slab listed again at the END, and a
+    Cell that demands both senses of one plane (it contains nothing), check the order and the contradiction rule."""
+    base = util.flat_from_xml(util.deck_text("three_shells", "surface"))["world"]
+    xs = np.arange(n_planes, dtype=np.float64)
+    world = dict(base)
+    world["surface_type"] = np.full(n_planes, 1, np.int32)  # MMC_SURF_PLANEX
+    prm = np.zeros((n_planes, 4))
+    prm[:, 0] = xs
+    world["surface_param"] = prm.reshape(-1)
+    begin, index, sense, material = [0], [], [], []
+
+    def cell(pairs, mat):
+        for s, sign in pairs:
+            index.append(s), sense.append(sign)
+        begin.append(len(index)), material.append(mat)
+
+    cell([(0, 1)], -1)                                   # x < plane 0 (void)
+    cell([(3, 0), (3, 1)], 0)                            # both senses of plane 3: contains nothing
+    for k in range(n_planes - 1):
+        cell([(k, 0), (k + 1, 1)], 0)                    # plane k <= x < plane k+1  (Contains is strict `<`)
+    cell([(n_planes - 1, 0)], -1)                        # beyond the last plane (void)
+    cell([(2, 0), (3, 1)], 0)                            # a copy of slab 2..3, later in the order: never chosen
+    n_cells = len(material)
+    world["cell_surface_begin"], world["cell_surface_index"], world["cell_surface_sense"] = begin, index, sense
+    world["cell_material"] = material
+    world["cell_field_kind"] = np.zeros(n_cells, np.int32)
+    world["cell_field_param"] = np.zeros(n_cells * 6)
+    w = capi.World(capi.FlatWorld(**world))
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.uniform(-2, n_planes + 1, 500), xs, xs - 1e-12, xs + 1e-12])
+    got, _, _ = w.geometry([(x, 0.3, -0.2) for x in pts], [(1, 0, 0)] * len(pts))
+    # expected: void 0 for x < 0; slab k -> cell 2 + k; beyond -> n_planes + 1
+    expected = np.where(pts < xs[0], 0, np.where(pts >= xs[-1], n_planes + 1, 2 + np.floor(pts).astype(int)))
+    assert got.tolist() == expected.tolist()
