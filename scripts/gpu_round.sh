@@ -18,13 +18,15 @@ echo "== bench $wl"; timeout 900 python bench.py --workload $wl --steps 5 --warm
 done
 echo "== bench fused schedule (for comparison)"; MMC_SCHEDULE=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-multigroup --no-cpu-baseline 2>$OUT/bench_fused.err | tee $OUT/bench_fused.json
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 1 --warmup 1 --histories-per-gpu 4194304 --no-cpu-baseline --no-multigroup > $OUT/bench_under_ncu.log 2>&1
 echo "== ncu full (S(a,b) kernel and flight kernel of a steady-state pass)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_tsl_kernel -s 6 -c 1 -o $OUT/prof_tsl \
   python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_tsl.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_flight_kernel -s 6 -c 1 -o $OUT/prof_flight \
   python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_flight.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_boundary_kernel -s 6 -c 1 -o $OUT/prof_boundary \
+  python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_boundary.log 2>&1
 if [ -z "${SKIP_MG:-}" ]; then
 echo "== ncu full (MG kernel)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fixed_source_kernel -s 1 -c 1 -o $OUT/prof_mg \
