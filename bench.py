@@ -149,10 +149,11 @@ ROOFLINE_NOTE = {
              "which keeps particle state in registers and the tables in L2/SMEM: real DRAM traffic is far below this "
              "model and the kernel is fp64-issue bound, see DESIGN.md",
     "event": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4) per step; a 'launch' is the "
-             "whole pass loop of one step (flight kernel + S(a,b) kernel per event, kernel_split has their CUDA-event "
+             "whole pass loop of one step (flight, boundary and S(a,b) kernel per event, kernel_split has their CUDA-event "
              "times and counts); particle state really streams through HBM here (traffic = ncu DRAM bytes). The "
-             "dominant S(a,b) kernel is bound by L1/shared-memory wavefronts of the table gathers, not by HBM: see "
-             "DESIGN.md and profiles/",
+             "dominant S(a,b) kernel is not HBM-bound: its first version sat at 88 % of peak L1 wavefronts (per-lane "
+             "table gathers); with the gathered rows in registers / shared memory it runs at 53 % of peak wavefronts "
+             "and 46 % of issue slots with 16 register-limited warps per SM: see DESIGN.md s4.1, s7 and profiles/",
 }
 
 
