@@ -44,6 +44,19 @@
 #define MMC_EV_TSL_THREADS (MMC_EV_TSL_ROWS_IN_REGS ? 512 : 768)
 #endif
 
+// Slot state is touched once per kernel and handed to the next kernel through L2: loads and stores bypass L1
+// (ld.global.cg / st.global.cg), which stays with the cross-section and S(a,b) table gathers.
+#ifndef MMC_STATE_CACHE_GLOBAL
+#define MMC_STATE_CACHE_GLOBAL 1
+#endif
+#if MMC_STATE_CACHE_GLOBAL
+#define MMC_LD(x) __ldcg(&(x))
+#define MMC_ST(x, v) __stcg(&(x), (v))
+#else
+#define MMC_LD(x) (x)
+#define MMC_ST(x, v) ((x) = (v))
+#endif
+
 namespace mmc {
 
 namespace {
@@ -174,13 +187,13 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   const uint32_t slot = q.alive[parity][i];
   const uint32_t n = q.count[parity];
   Particle p;
-  p.event = st.event[slot];
-  p.px = st.px[slot], p.py = st.py[slot], p.pz = st.pz[slot];
-  p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
-  p.energy = st.energy[slot];
+  p.event = MMC_LD(st.event[slot]);
+  p.px = MMC_LD(st.px[slot]), p.py = MMC_LD(st.py[slot]), p.pz = MMC_LD(st.pz[slot]);
+  p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
+  p.energy = MMC_LD(st.energy[slot]);
   p.group = 0;
-  p.rng.x = st.rng[slot];
-  p.cell = st.cell[slot];
+  p.rng.x = MMC_LD(st.rng[slot]);
+  p.cell = MMC_LD(st.cell[slot]);
   p.surface = -1;  // written only by a crossing; tallies read it in the boundary kernel
   if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = 0;  // chunk counter of this pass's S(a,b) kernel
   if (first >= n) return;  // CTA-uniform
@@ -196,8 +209,8 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   dq.head = 0;
   dq.count = 0;
   if (alive && has_secondaries) {
-    dq.head = st.dq_head[slot];
-    dq.count = st.dq_count[slot];
+    dq.head = MMC_LD(st.dq_head[slot]);
+    dq.count = MMC_LD(st.dq_count[slot]);
   }
   ThreadCounters c;
   StepOut o;
@@ -209,19 +222,19 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
     // p.cell >= 0: the boundary kernel looked the Cell up at birth and after every crossing
     transport_step<kTracking, true, false, true, false, true>(w, p, dq, o);
     count_event(c, p, o);
-    st.px[slot] = p.px, st.py[slot] = p.py, st.pz[slot] = p.pz;
-    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
-    st.energy[slot] = p.energy;
-    st.rng[slot] = p.rng.x;
-    st.event[slot] = p.event;
-    if (o.need_cross) st.surface[slot] = p.surface;
+    MMC_ST(st.px[slot], p.px), MMC_ST(st.py[slot], p.py), MMC_ST(st.pz[slot], p.pz);
+    MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
+    MMC_ST(st.energy[slot], p.energy);
+    MMC_ST(st.rng[slot], p.rng.x);
+    MMC_ST(st.event[slot], p.event);
+    if (o.need_cross) MMC_ST(st.surface[slot], p.surface);
     if (has_secondaries) {
-      st.dq_head[slot] = dq.head;
-      st.dq_count[slot] = dq.count;
+      MMC_ST(st.dq_head[slot], dq.head);
+      MMC_ST(st.dq_count[slot], dq.count);
     }
     if (o.need_tsl) {
-      st.tsl_T[slot] = o.tsl_T;
-      st.tsl_off[slot] = o.tsl_off;
+      MMC_ST(st.tsl_T[slot], o.tsl_T);
+      MMC_ST(st.tsl_off[slot], o.tsl_off);
     }
   }
   // ---- stream compaction into the three queues of this pass
@@ -272,23 +285,23 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
   const bool has_secondaries = run.secondary_capacity > 1;
 
   Particle p;
-  p.event = valid ? st.event[slot] : kEvRetired;
-  p.px = st.px[slot], p.py = st.py[slot], p.pz = st.pz[slot];
-  p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
-  p.energy = st.energy[slot];
+  p.event = valid ? MMC_LD(st.event[slot]) : kEvRetired;
+  p.px = MMC_LD(st.px[slot]), p.py = MMC_LD(st.py[slot]), p.pz = MMC_LD(st.pz[slot]);
+  p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
+  p.energy = MMC_LD(st.energy[slot]);
   p.group = 0;
-  p.rng.x = st.rng[slot];
-  p.cell = st.cell[slot];
-  p.surface = st.surface[slot];
-  uint32_t n_pending = run.n_estimators ? st.n_pending[slot] : 0u;
+  p.rng.x = MMC_LD(st.rng[slot]);
+  p.cell = MMC_LD(st.cell[slot]);
+  p.surface = MMC_LD(st.surface[slot]);
+  uint32_t n_pending = run.n_estimators ? MMC_LD(st.n_pending[slot]) : 0u;
   SiteDeque dq;
   dq.slots = site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
   dq.mask = run.secondary_capacity - 1;
   dq.head = 0;
   dq.count = 0;
   if (valid && has_secondaries) {
-    dq.head = st.dq_head[slot];
-    dq.count = st.dq_count[slot];
+    dq.head = MMC_LD(st.dq_head[slot]);
+    dq.count = MMC_LD(st.dq_count[slot]);
   }
   ThreadCounters c;
 
@@ -380,17 +393,17 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
     }
   }
   if (valid) {
-    st.px[slot] = p.px, st.py[slot] = p.py, st.pz[slot] = p.pz;
-    st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
-    st.energy[slot] = p.energy;
-    st.rng[slot] = p.rng.x;
-    st.cell[slot] = p.cell;
-    st.surface[slot] = p.surface;
-    st.event[slot] = p.event;
-    if (run.n_estimators) st.n_pending[slot] = n_pending;
+    MMC_ST(st.px[slot], p.px), MMC_ST(st.py[slot], p.py), MMC_ST(st.pz[slot], p.pz);
+    MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
+    MMC_ST(st.energy[slot], p.energy);
+    MMC_ST(st.rng[slot], p.rng.x);
+    MMC_ST(st.cell[slot], p.cell);
+    MMC_ST(st.surface[slot], p.surface);
+    MMC_ST(st.event[slot], p.event);
+    if (run.n_estimators) MMC_ST(st.n_pending[slot], n_pending);
     if (has_secondaries) {
-      st.dq_head[slot] = dq.head;
-      st.dq_count[slot] = dq.count;
+      MMC_ST(st.dq_head[slot], dq.head);
+      MMC_ST(st.dq_count[slot], dq.count);
     }
   }
   flush_counters_cta(c, has_secondaries, s_packed, counter_replicas);
@@ -448,24 +461,24 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     if (i < n) {  // no early `continue`: every lane must come back to the shuffle above
     const uint32_t slot = q.tsl[i];
     Particle p;
-    p.energy = st.energy[slot];
-    p.rng.x = st.rng[slot];
-    const double T = st.tsl_T[slot];
-    const TslTable& t = *w.at<TslTable>(st.tsl_off[slot]);
+    p.energy = MMC_LD(st.energy[slot]);
+    p.rng.x = MMC_LD(st.rng[slot]);
+    const double T = MMC_LD(st.tsl_T[slot]);
+    const TslTable& t = *w.at<TslTable>(MMC_LD(st.tsl_off[slot]));
     bool error = false;
     double mu = 0, E_p = 0;
     ce::tsl_sample(w, t, p.rng, p.energy, T, error, rows, mu, E_p);
     if (!error) {
       // the direction is only needed now: it stays in memory while the sampler's state fills the registers
-      p.dx = st.dx[slot], p.dy = st.dy[slot], p.dz = st.dz[slot];
+      p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
       ce::particle_scatter(p, mu, E_p);
-      st.dx[slot] = p.dx, st.dy[slot] = p.dy, st.dz[slot] = p.dz;
-      st.energy[slot] = p.energy;
+      MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
+      MMC_ST(st.energy[slot], p.energy);
     }
-    st.rng[slot] = p.rng.x;
+    MMC_ST(st.rng[slot], p.rng.x);
     if (error) {
       // the reference throws here (-> std::terminate); the flight kernel counted the collision already
-      st.event[slot] = MMC_EV_CAPTURE;
+      MMC_ST(st.event[slot], MMC_EV_CAPTURE);
       unsigned long long* mine = counter_replicas + (blockIdx.x % kCounterReplicas) * kNumCounters;
       atomicAdd(mine + 3, ~0ull);  // n_collisions - 1
       atomicAdd(mine + 11, 1ull);  // n_physics_errors + 1
