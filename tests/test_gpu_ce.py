@@ -155,6 +155,28 @@ def test_ce_schedules_agree_at_scale(tmp_path):
             assert c == results[0][2]
 
 
+def test_ce_lost_particles_are_counted_alike_by_every_schedule(tables):
+    """A slab whose far void is missing (crossing the right plane finds no Cell) and, second, a source outside every
+    Cell: World::FindCellContaining throws in the reference; here the run reports MMC_ERR_LOST_PARTICLE and the
+    fused, event-split and event-only schedules count the same events, crossings and lost particles."""
+    text = ce_decks.slab_deck(tables, histories=3000, threads=1)
+    last_void = text.rindex("  <void>")
+    no_far_void = text[:last_void] + text[text.index("</void>\n", last_void) + len("</void>\n"):]
+    outside = text.replace('<constant x="0" y="0" z="0"/>', '<constant x="-5" y="0" z="0"/>', 1)
+    outside = outside[:outside.index("  <void>")] + outside[outside.index("</void>\n") + len("</void>\n"):]
+    for deck in (no_far_void, outside):
+        seen = []
+        for schedule in (capi.SCHEDULE_FUSED, capi.SCHEDULE_EVENT, capi.SCHEDULE_EVENT_ONLY):
+            drv = capi.Driver(text=deck)
+            drv.set_options(schedule=schedule, event_slots=777)
+            with pytest.raises(capi.MinimcError) as e:
+                drv.solve()
+            assert e.value.status == capi.ERR_LOST_PARTICLE
+            seen.append(drv.counters())
+        assert seen[0]["n_lost"] > 0 and seen[0]["n_histories"] == 3000
+        assert seen[1] == seen[0] and seen[2] == seen[0]
+
+
 def test_ce_resample_limit_is_reported(tables):
     """A source far above every table (20 MeV neutron in the slab) still runs; an absurd temperature below every
     partition's grid makes BetaPartition::Evaluate divide 0 by 0 and the resample limit trip: the reference throws
