@@ -526,7 +526,7 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
       if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "launch_event_pass: %s", cudaGetErrorString(err));
     }
-    w->last_launches += 3 * batch;
+    w->last_launches += static_cast<uint64_t>(event_kernels_per_pass()) * batch;
     cudaError_t err = cudaMemcpyAsync(w->h_event_counts, b.q.count, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p.stream);
     if (err == cudaSuccess)
       err = cudaMemcpyAsync(w->h_event_counts + 4, w->d_next, sizeof(unsigned long long), cudaMemcpyDeviceToHost, p.stream);

@@ -3,13 +3,14 @@
 // The fused kernel (kernels.cu) keeps a particle in registers for its whole life.
 // For the S(a,b) decks that puts ~14 k instructions (230 KB) of divergent code in
 // one kernel: ncu shows warps waiting on instruction fetch as often as on memory.
-// Here one PASS advances every live history by one event with three small kernels:
+// Here one PASS advances every live history by one event in three small pieces of code (two launches: the boundary
+// work runs as the prologue of the persistent S(a,b) kernel unless built with -DMMC_EV_MERGE_BOUNDARY=0):
 //
 //   event_flight_kernel    cross-section lookup, distance to collision and to the nearest surface, the flight;
 //                          at a collision: nuclide and reaction choice, capture / free-gas scatter / fission.
 //                          A collision that chose thermal scattering is not sampled here (-> S(a,b) queue); a
 //                          particle that reached a surface, or died, is not finished here (-> boundary queue).
-//   event_boundary_kernel  dense over the boundary queue: Cell lookup after a crossing, leak, tallies; next
+//   boundary_chunk         dense over the boundary queue: Cell lookup after a crossing, leak, tallies; next
 //                          particle of the history's bank, next history (Source::Sample), retirement of the slot.
 //   event_tsl_kernel       ThermalScattering::Scatter (SampleBeta, SampleAlpha, Particle::Scatter) for the
 //                          S(a,b) queue -- every lane of every warp runs the POD sampler.
@@ -100,7 +101,7 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
   if (i < kCounterReplicas * kNumCounters) counter_replicas[i] = 0;
   if (i == 0) {
     q.count[0] = n_slots;
-    q.count[1] = q.count[2] = q.count[3] = q.count[4] = q.count[5] = q.count[6] = 0;
+    q.count[1] = q.count[2] = q.count[3] = q.count[4] = q.count[5] = q.count[6] = q.count[7] = 0;
   }
 }
 
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   p.rng.x = MMC_LD(st.rng[slot]);
   p.cell = MMC_LD(st.cell[slot]);
   p.surface = -1;  // written only by a crossing; tallies read it in the boundary kernel
-  if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = 0;  // chunk counter of this pass's S(a,b) kernel
+  if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = q.count[7] = 0;  // chunk counters of this pass's S(a,b) kernel
   if (first >= n) return;  // CTA-uniform
   const bool valid = i < n;
   const WorldView w(world_g, &header);
@@ -257,31 +258,27 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
 //     EstimatorSetProxy::Score (:74) -- `current` estimators score nothing else;
 //   * a dead particle (captured or fissioned in this pass's flight, leaked just above, or dead since an earlier
 //     pass): the next particle of the slot's history from its bank (FixedSource.cpp:63-71), else a new history
-//     (one atomic per CTA claims the indices), Source::Sample, and the Cell of the newborn (TransportMethod.cpp:55);
+//     (one atomic per warp claims the indices), Source::Sample, and the Cell of the newborn (TransportMethod.cpp:55);
 //     a slot that finds no history left retires.
 // In a steady-state single_zone pass 8 % of the live slots come here (4 % crossings, 4 % history ends); inside the
 // flight kernel these branches ran with one or two lanes of a warp while the others waited.
-template <int kTracking>
-__global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
-    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
-    const double* __restrict__ bounds, const __grid_constant__ EventState st, const __grid_constant__ EventQueues q,
-    uint32_t pass, BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch,
-    unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
-    unsigned long long* counter_replicas) {
-  __shared__ uint32_t s_claims[kWarpsPerBlock];
-  __shared__ unsigned long long s_claim_base;
-  __shared__ uint4 s_packed[kWarpsPerBlock];
+//
+// boundary_chunk: one warp, 32 consecutive queue entries (lane i: entry base + i; `valid` false past the end).
+// Every lane of the warp must call it (ballots, REDUX).
+struct BoundaryArgs {
+  const double* bounds;
+  BankSite* site_scratch;
+  uint2* pending_scratch;
+  unsigned long long* next_history;
+  unsigned long long* scores;
+  unsigned long long* square_scores;
+};
 
-  const uint32_t parity = pass & 1u;
-  const uint32_t n = q.count[5u + parity];
-  const uint32_t first = blockIdx.x * kFlightThreads;
-  if (first >= n) return;  // CTA-uniform
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void boundary_chunk(
+    const WorldView& w, const RunSpec& run, const EventState& st, const BoundaryArgs& a, uint32_t slot, bool valid,
+    unsigned long long* counter_replica) {
+  const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lanes_below = (1u << lane) - 1u;
-  const uint32_t i = first + threadIdx.x;
-  const bool valid = i < n;
-  const uint32_t slot = valid ? q.boundary[i] : 0u;
-  const WorldView w(world_g, &header);
   const bool has_secondaries = run.secondary_capacity > 1;
 
   Particle p;
@@ -295,7 +292,7 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
   p.surface = MMC_LD(st.surface[slot]);
   uint32_t n_pending = run.n_estimators ? MMC_LD(st.n_pending[slot]) : 0u;
   SiteDeque dq;
-  dq.slots = site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
+  dq.slots = a.site_scratch + static_cast<size_t>(slot) * run.secondary_capacity;
   dq.mask = run.secondary_capacity - 1;
   dq.head = 0;
   dq.count = 0;
@@ -316,10 +313,10 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
     c.crossings++;  // count_event: surface_cross or leak (a lost particle is recorded as a leak)
     c.lost += lost;
   }
-  uint2* pending = pending_scratch + static_cast<size_t>(slot) * run.pending_capacity;
+  uint2* pending = a.pending_scratch + static_cast<size_t>(slot) * run.pending_capacity;
   for (int32_t e = 0; e < run.n_estimators; e++) {
     uint64_t bin = 0;
-    const bool hit = crossing && !lost && estimator_score<true>(run.estimators[e], bounds, p, bin);
+    const bool hit = crossing && !lost && estimator_score<true>(run.estimators[e], a.bounds, p, bin);
     const unsigned hit_mask = __ballot_sync(kFull, hit);
     if (hit) {
       // incremental CommitHistory: the k-th hit of a history in a bin adds 1 and 2k - 1 (see kernels.cu)
@@ -338,8 +335,8 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
       const unsigned peers = __match_any_sync(hit_mask, bin);
       const uint32_t sq = __reduce_add_sync(peers, 2u * k + 1u);
       if (lane == static_cast<uint32_t>(__ffs(peers) - 1)) {
-        atomicAdd(scores + bin, static_cast<unsigned long long>(__popc(peers)));
-        atomicAdd(square_scores + bin, static_cast<unsigned long long>(sq));
+        atomicAdd(a.scores + bin, static_cast<unsigned long long>(__popc(peers)));
+        atomicAdd(a.square_scores + bin, static_cast<unsigned long long>(sq));
       }
     }
   }
@@ -355,22 +352,17 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
   }
   const bool need = valid && !alive;
   const unsigned need_mask = __ballot_sync(kFull, need);
-  if (lane == 0) s_claims[warp] = __popc(need_mask);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t total = 0;
-    for (int k = 0; k < kWarpsPerBlock; k++) total += s_claims[k];
-    unsigned long long base = 0;
-    if (total) {
-      base = *reinterpret_cast<volatile unsigned long long*>(next_history);
-      if (base < run.n_histories) base = atomicAdd(next_history, static_cast<unsigned long long>(total));
+  unsigned long long claim_base = 0;
+  if (need_mask) {
+    if (lane == 0) {
+      claim_base = *reinterpret_cast<volatile unsigned long long*>(a.next_history);
+      if (claim_base < run.n_histories)
+        claim_base = atomicAdd(a.next_history, static_cast<unsigned long long>(__popc(need_mask)));
     }
-    s_claim_base = base;
+    claim_base = __shfl_sync(kFull, claim_base, 0);
   }
-  __syncthreads();
   if (need) {
-    uint32_t total;
-    const uint64_t idx = s_claim_base + warp_prefix(s_claims, warp, total) + __popc(need_mask & lanes_below);
+    const uint64_t idx = claim_base + __popc(need_mask & lanes_below);
     if (idx < run.n_histories) {
       n_pending = 0;  // a new scoring proxy starts empty: FixedSource.cpp:48
       sample_source(run.source, run.seed0 + run.first_history + idx, p);
@@ -406,8 +398,42 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
       MMC_ST(st.dq_count[slot], dq.count);
     }
   }
-  flush_counters_cta(c, has_secondaries, s_packed, counter_replicas);
+  // ---- counters: packed, one warp reduction per word, lane 0 adds the non-zero ones to this warp's replica
+  const uint32_t pa = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
+  const uint32_t pb = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
+  const uint32_t pd = c.scores | (c.capacity << 16);
+  const uint32_t sa = __reduce_add_sync(kFull, pa), sb = __reduce_add_sync(kFull, pb), sd = __reduce_add_sync(kFull, pd);
+  if (lane == 0) {
+    const uint32_t sums[kNumCounters] = {sb & 0xffu, (sb >> 8) & 0xffu, sa & 0xffu, (sa >> 8) & 0xffu, (sa >> 16) & 0xffu, sa >> 24,
+                                         sd & 0xffffu, 0u, 0u, (sb >> 16) & 0xffu, sd >> 16, sb >> 24};
+#pragma unroll
+    for (int k = 0; k < kNumCounters; k++)
+      if (sums[k]) atomicAdd(counter_replica + k, static_cast<unsigned long long>(sums[k]));
+  }
 }
+
+// MMC_EV_MERGE_BOUNDARY = 1 (default): the warps of the persistent S(a,b) kernel work off the boundary queue first, then
+// the S(a,b) queue -- the boundary work is a short latency chain over few slots (28 us as a kernel of its own,
+// 12 % issue slots); inside the persistent kernel it overlaps with the S(a,b) sampling of the other warps.
+// 0: a kernel of its own between the flight and the S(a,b) kernel (kept for profiling it in isolation).
+#ifndef MMC_EV_MERGE_BOUNDARY
+#define MMC_EV_MERGE_BOUNDARY 1
+#endif
+
+#if !MMC_EV_MERGE_BOUNDARY
+__global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
+    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
+    const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
+    const __grid_constant__ BoundaryArgs args, unsigned long long* counter_replicas) {
+  const uint32_t n = q.count[5u + (pass & 1u)];
+  const uint32_t i = blockIdx.x * kFlightThreads + threadIdx.x;
+  if ((i & ~31u) >= n) return;  // warp-uniform
+  const bool valid = i < n;
+  const WorldView w(world_g, &header);
+  boundary_chunk(w, run, st, args, valid ? q.boundary[i] : 0u, valid,
+                 counter_replicas + ((i >> 5) % kCounterReplicas) * kNumCounters);
+}
+#endif
 
 // ThermalScattering::Scatter (ThermalScattering.cpp:159-171) for the slots the flight kernel queued.
 //
@@ -423,8 +449,9 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
 // Warps claim chunks of 32 queue entries from a counter; state loads and stores are coalesced over the compacted queue.
 template <bool kSharedSc>
 __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
-    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ EventState st,
-    const __grid_constant__ EventQueues q, uint32_t pass, unsigned long long* counter_replicas) {
+    const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
+    const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
+    const __grid_constant__ BoundaryArgs args, unsigned long long* counter_replicas) {
   extern __shared__ __align__(16) char smem[];
   [[maybe_unused]] double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
   char* s_sc = smem + kTslRowBytes;
@@ -436,7 +463,9 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
   }
   const uint32_t n = q.count[2u + parity];
   constexpr uint32_t kWarps = kTslThreads / 32;
+#if !MMC_EV_MERGE_BOUNDARY
   if (blockIdx.x * kWarps * 32u >= n) return;  // CTA-uniform: not even the first warp has work
+#endif
   const WorldView w(world_g, &header);
   if (kSharedSc) {
     const uint4* src = reinterpret_cast<const uint4*>(world_g + w.h->off_sc_arena);
@@ -445,6 +474,21 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     __syncthreads();
   }
   const uint32_t lane = threadIdx.x & 31u;
+#if MMC_EV_MERGE_BOUNDARY
+  {
+    // the boundary queue first: chunks of 32 entries claimed from a counter (zeroed by the flight kernel)
+    const uint32_t n_boundary = q.count[5u + parity];
+    unsigned long long* replica = counter_replicas + ((blockIdx.x * kWarps + (threadIdx.x >> 5)) % kCounterReplicas) * kNumCounters;
+    while (true) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&q.count[7], 32u);
+      base = __shfl_sync(kFull, base, 0);
+      if (base >= n_boundary) break;
+      const bool valid = base + lane < n_boundary;
+      boundary_chunk(w, run, st, args, valid ? q.boundary[base + lane] : 0u, valid, replica);
+    }
+  }
+#endif
 #if MMC_EV_TSL_ROWS_IN_REGS
   ce::RegisterRows<kSharedSc> rows(s_sc, w.h->off_sc_arena);
 #else
@@ -521,25 +565,30 @@ cudaError_t launch_event_pass(
     event_flight_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
         world_d, header, run, st, q, pass, site_scratch, counter_replicas);
   if (marks) cudaEventRecord(marks[0], stream);
-  if (run.tracking == MMC_TRACK_CELL_DELTA)
-    event_boundary_kernel<MMC_TRACK_CELL_DELTA><<<blocks, kFlightThreads, 0, stream>>>(
-        world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
-        counter_replicas);
-  else
-    event_boundary_kernel<MMC_TRACK_SURFACE><<<blocks, kFlightThreads, 0, stream>>>(
-        world_d, header, run, bounds_d, st, q, pass, site_scratch, pending_scratch, next_history, scores, square_scores,
-        counter_replicas);
+  BoundaryArgs args;
+  args.bounds = bounds_d;
+  args.site_scratch = site_scratch;
+  args.pending_scratch = pending_scratch;
+  args.next_history = next_history;
+  args.scores = scores;
+  args.square_scores = square_scores;
+#if !MMC_EV_MERGE_BOUNDARY
+  event_boundary_kernel<<<blocks, kFlightThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+#endif
   if (marks) cudaEventRecord(marks[1], stream);
-  // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queue can feed
+  // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queues can feed
   const uint32_t per_cta = kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
   if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
   if (tsl.shared_sc)
-    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(world_d, header, st, q, pass, counter_replicas);
+    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(
+        world_d, header, run, st, q, pass, args, counter_replicas);
   else
-    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, header, st, q, pass, counter_replicas);
+    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
   return cudaGetLastError();
 }
+
+int event_kernels_per_pass() { return MMC_EV_MERGE_BOUNDARY ? 2 : 3; }
 
 cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out) {
   out.sm_count = sm_count;

@@ -84,7 +84,7 @@ struct EventQueues {
   uint32_t* alive[2];   // compacted slot indices, ping-pong between passes
   uint32_t* tsl;        // slots whose collision awaits S(a,b) sampling in this pass
   uint32_t* boundary;   // slots whose particle is on a surface or dead: Cell lookup, tallies, next particle / history
-  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity), [4] chunk counter of the S(a,b) kernel, [5..6] boundary counts
+  unsigned int* count;  // [0..1] alive counts, [2..3] tsl counts (by pass parity), [4] chunk counter of the S(a,b) kernel, [5..6] boundary counts, [7] chunk counter of the boundary queue
 };
 
 constexpr int kCounterReplicas = 64;
@@ -108,6 +108,7 @@ cudaError_t launch_event_pass(
     unsigned long long* next_history, unsigned long long* scores, unsigned long long* square_scores,
     unsigned long long* counter_replicas, const EventTslConfig& tsl, cudaStream_t stream,
     const cudaEvent_t* marks = nullptr);  // profile mode: marks[0] after the flight kernel, marks[1] after the boundary kernel
+int event_kernels_per_pass();
 // shared-memory plan of the S(a,b) kernel for a world (opts the kernels into their dynamic shared memory)
 cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint32_t sm_count, EventTslConfig& out);
 cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_counters* counters, cudaStream_t stream);
