@@ -777,6 +777,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
         o.off_cdf = b.add(q.cdf, q.n_cdf);
         o.off_cdf_hint = hint(q.cdf, q.n_cdf);
         o.off_T = b.add(q.temperature, q.n_temperature);
+        o.off_T_hint = hint(q.temperature, q.n_temperature);
         o.off_scaled_cdf_modes = sc_offsets[sc_next++];  // in the arena, same traversal order
         o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
         o.grid_begin = static_cast<uint32_t>(concatenated.size());
@@ -811,6 +812,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           tt.off_E = b.add(t.energy, t.n_energy);
           tt.off_E_hint = hint(t.energy, t.n_energy);
           tt.off_T = b.add(t.temperature, t.n_temperature);
+          tt.off_T_hint = hint(t.temperature, t.n_temperature);
           // S[r] * scatter_xs_E[E][r]: the first product of EvaluateInelastic (ThermalScattering.cpp:264-267)
           std::vector<double> xs_SE(t.n_energy * t.rank);
           for (uint64_t e = 0; e < t.n_energy; e++)

@@ -116,7 +116,8 @@ struct TslPartition {
   uint32_t off_cdf_hint;   // SearchHint of cdf, 0 = none
   uint32_t off_modes;      // double[n_grid][n_T][rank]
   uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
-  uint32_t pad[2];
+  uint32_t off_T_hint;     // SearchHint of T, 0 = none
+  uint32_t pad;
 };
 
 // ThermalScattering
@@ -129,6 +130,8 @@ struct TslTable {
   uint32_t n_Es, off_Es;        // concatenated incident energies of the beta partitions (ThermalScattering::Es)
   uint32_t n_betas, off_betas;  // concatenated betas of the alpha partitions (ThermalScattering::betas)
   uint32_t off_betas_hint;      // SearchHints of E / Es / betas: off_E_hint, off_Es_hint, off_betas_hint
+  uint32_t off_T_hint;          // SearchHint of T
+  uint32_t pad_hint;
   double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
 };
 
