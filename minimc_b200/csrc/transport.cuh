@@ -101,9 +101,15 @@ __device__ __forceinline__ void isotropic_direction(Rng& rng, double& x, double&
 __device__ __forceinline__ void normalize(double& x, double& y, double& z) {
   // Point::Normalize: *this /= sqrt(Dot(*this)), Point.cpp:44-47
   const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-  x = __ddiv_rn(x, n);
-  y = __ddiv_rn(y, n);
-  z = __ddiv_rn(z, n);
+  // (+-0) / n == (+-0) for every n > 0.  The cross product with a coordinate axis (rotate_direction) always has one
+  // component that is exactly zero, and a zero QUOTIENT sends CUDA's fp64 division down its slow path (a ~300
+  // instruction subroutine: 5 % of the S(a,b) kernel's instructions).  Such a lane divides n by n instead (fast path)
+  // and keeps its zero: same result, no branch.
+  const bool zx = x == 0.0 && n > 0.0, zy = y == 0.0 && n > 0.0, zz = z == 0.0 && n > 0.0;
+  const double qx = __ddiv_rn(zx ? n : x, n), qy = __ddiv_rn(zy ? n : y, n), qz = __ddiv_rn(zz ? n : z, n);
+  x = zx ? x : qx;
+  y = zy ? y : qy;
+  z = zz ? z : qz;
 }
 
 // Direction(const Direction& d, mu, phi): Point.cpp:98-121
