@@ -103,10 +103,13 @@ __device__ __forceinline__ void normalize(double& x, double& y, double& z) {
   const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
   // (+-0) / n == (+-0) for every n > 0.  The cross product with a coordinate axis (rotate_direction) always has one
   // component that is exactly zero, and a zero QUOTIENT sends CUDA's fp64 division down its slow path (a ~300
-  // instruction subroutine: 5 % of the S(a,b) kernel's instructions).  Such a lane divides n by n instead (fast path)
+  // instruction subroutine: 5 % of the S(a,b) kernel's instructions).  Such a lane divides 0 + n by n instead (fast path)
   // and keeps its zero: same result, no branch.
   const bool zx = x == 0.0 && n > 0.0, zy = y == 0.0 && n > 0.0, zz = z == 0.0 && n > 0.0;
-  const double qx = __ddiv_rn(zx ? n : x, n), qy = __ddiv_rn(zy ? n : y, n), qz = __ddiv_rn(zz ? n : z, n);
+  // (the dividend is formed by an addition, not a select: the compiler folds `zx ? n : x` back to x because the
+  // quotient of such a lane is not used)
+  const double qx = __ddiv_rn(__dadd_rn(x, zx ? n : 0.0), n), qy = __ddiv_rn(__dadd_rn(y, zy ? n : 0.0), n),
+               qz = __ddiv_rn(__dadd_rn(z, zz ? n : 0.0), n);
   x = zx ? x : qx;
   y = zy ? y : qy;
   z = zz ? z : qz;
