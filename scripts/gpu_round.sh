@@ -25,8 +25,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:even
   python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_tsl.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_flight_kernel -s 6 -c 1 -o $OUT/prof_flight \
   python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_flight.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_boundary_kernel -s 6 -c 1 -o $OUT/prof_boundary \
-  python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_boundary.log 2>&1
 if [ -z "${SKIP_MG:-}" ]; then
 echo "== ncu full (MG kernel)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:fixed_source_kernel -s 1 -c 1 -o $OUT/prof_mg \
