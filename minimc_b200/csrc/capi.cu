@@ -625,7 +625,31 @@ uint64_t mmc_estimator_size(const mmc_estimator_desc* e) {
 
 namespace {
 // Flattens a validated world description into the device image (world_blob.h).
-int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& header_out, bool& has_fission_out) {
+// `jobs`: the dense reconstruction tables to expand on the device after the image is uploaded (world_blob.h
+// DenseJob); their space is the device-only tail behind the image.
+int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& header_out, bool& has_fission_out,
+                     std::vector<DenseJob>& jobs) {
+  jobs.clear();
+  // dense tables: offsets are known relative to the tail while the image is still growing; the fields that hold them
+  // are patched once the image's size is final
+  struct DensePatch { size_t field_at; uint32_t tail_offset; };
+  std::vector<DensePatch> dense_patches;
+  uint64_t dense_total = 0, dense_budget = 512ull << 20;
+  if (const char* mb = std::getenv("MMC_TSL_DENSE_MB")) dense_budget = std::strtoull(mb, nullptr, 10) << 20;
+  bool dense_complete = true;
+  int dense_tables = 0;
+  // reserves n doubles in the tail; false when over the budget
+  auto reserve_dense = [&](uint64_t n_doubles, uint32_t& tail_offset) {
+    const uint64_t bytes = (n_doubles * 8 + 15) & ~15ull;
+    if (n_doubles == 0 || dense_total + bytes > dense_budget) {
+      dense_complete = false;
+      return false;
+    }
+    tail_offset = static_cast<uint32_t>(dense_total);
+    dense_total += bytes;
+    dense_tables++;
+    return true;
+  };
   const int G = d->n_groups;
   const int nnz_cell = d->cell_surface_begin[d->n_cells];
   const int nnz_mat = d->n_materials ? d->material_nuclide_begin[d->n_materials] : 0;
@@ -765,8 +789,10 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
       b.pad();
       h.sc_arena_bytes = static_cast<uint32_t>(b.bytes.size()) - h.off_sc_arena;
     }
-    auto partitions = [&b, &sc_offsets, &sc_next, &hint](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
+    auto partitions = [&](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
       std::vector<TslPartition> out(n);
+      std::vector<uint32_t> tail(n, 0);
+      std::vector<char> expanded(n, 0);
       for (int i = 0; i < n; i++) {
         const mmc_tsl_partition& q = p[i];
         TslPartition& o = out[i];
@@ -782,8 +808,16 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
         o.off_modes = b.add(q.grid_T_modes, q.n_grid * q.n_temperature * q.rank);
         o.grid_begin = static_cast<uint32_t>(concatenated.size());
         concatenated.insert(concatenated.end(), q.grid, q.grid + q.n_grid);
+        o.off_dense = 0;
+        if (reserve_dense(q.n_grid * q.n_cdf * q.n_temperature, tail[i])) {
+          expanded[i] = 1;
+          jobs.push_back(DenseJob{o.off_scaled_cdf_modes, o.off_modes, tail[i], o.n_grid, o.n_cdf, o.n_T, o.rank});
+        }
       }
-      return b.add(out.data(), out.size());
+      const uint32_t at = b.add(out.data(), out.size());
+      for (int i = 0; i < n; i++)
+        if (expanded[i]) dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_dense), tail[i]});
+      return at;
     };
     std::vector<CeNuclide> nuclides(d->n_nuclides);
     for (int n = 0; n < d->n_nuclides; n++) {
@@ -834,15 +868,26 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           tt.alpha_cutoff = t.alpha_cutoff;
           tt.awr = t.awr;
           tt.cutoff_energy = t.energy[t.n_energy - 1];  // ThermalScattering.hpp:125-126
+          uint32_t xs_tail = 0;
+          const bool xs_expanded = reserve_dense(t.n_energy * t.n_temperature, xs_tail);
+          if (xs_expanded) jobs.push_back(DenseJob{tt.off_xs_SE, tt.off_xs_T, xs_tail, 1u, tt.n_E, tt.n_T, tt.rank});
           xr.off_tsl = b.add(&tt, 1);
+          if (xs_expanded) dense_patches.push_back({xr.off_tsl + offsetof(TslTable, off_xs_dense), xs_tail});
         }
       }
     }
     h.off_ce_nuclides = b.add(nuclides.data(), nuclides.size());
   }
   b.pad();
-  if (b.bytes.size() > 0xfffffff0ull) return fail(MMC_ERR_INVALID, "world tables exceed 4 GiB");
+  if (b.bytes.size() + dense_total > 0xfffffff0ull) return fail(MMC_ERR_INVALID, "world tables exceed 4 GiB");
   h.total_bytes = static_cast<uint32_t>(b.bytes.size());
+  h.dense_bytes = static_cast<uint32_t>(dense_total);
+  h.tsl_all_dense = dense_tables > 0 && dense_complete;
+  for (const DensePatch& patch : dense_patches) {
+    const uint32_t absolute = h.total_bytes + patch.tail_offset;
+    std::memcpy(b.bytes.data() + patch.field_at, &absolute, sizeof(uint32_t));
+  }
+  for (DenseJob& job : jobs) job.off_out += h.total_bytes;
   b.header() = h;
   header_out = h;
   has_fission_out = has_fission;
@@ -861,7 +906,8 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   BlobBuilder b;
   WorldHeader h{};
   bool has_fission = false;
-  if (int s = build_world_blob(d, b, h, has_fission)) return s;
+  std::vector<DenseJob> dense_jobs;
+  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs)) return s;
 
   auto* w = new mmc_world;
   w->device = device;
@@ -870,12 +916,14 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   w->has_fission = has_fission;
   cudaDeviceProp prop{};
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
-  if (e == cudaSuccess) e = cudaMalloc(&w->d_blob, w->blob_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&w->d_blob, static_cast<size_t>(w->blob_bytes) + h.dense_bytes);
   if (e == cudaSuccess) e = cudaMallocHost(&w->h_blob, w->blob_bytes);  // pinned staging copy of the image
   if (e == cudaSuccess) std::memcpy(w->h_blob, b.bytes.data(), w->blob_bytes);
   if (e == cudaSuccess) e = cudaMemcpy(w->d_blob, w->h_blob, w->blob_bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&w->d_next, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
   if (e != cudaSuccess) {
     mmc_world_destroy(w);
     return fail(MMC_ERR_CUDA, "mmc_world_create: %s", cudaGetErrorString(e));
@@ -892,13 +940,16 @@ int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
   BlobBuilder b;
   WorldHeader h{};
   bool has_fission = false;
-  if (int s = build_world_blob(d, b, h, has_fission)) return s;
-  if (h.total_bytes != w->blob_bytes || has_fission != w->has_fission || h.n_groups != w->header.n_groups)
+  std::vector<DenseJob> dense_jobs;
+  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs)) return s;
+  if (h.total_bytes != w->blob_bytes || h.dense_bytes != w->header.dense_bytes || has_fission != w->has_fission ||
+      h.n_groups != w->header.n_groups)
     return fail(MMC_ERR_INVALID, "mmc_world_update: the new tables have a different shape (%u bytes, world holds %u): "
                 "create a new world", h.total_bytes, w->blob_bytes);
   MMC_CUDA(cudaSetDevice(w->device));
   std::memcpy(w->h_blob, b.bytes.data(), w->blob_bytes);
   MMC_CUDA(cudaMemcpyAsync(w->d_blob, w->h_blob, w->blob_bytes, cudaMemcpyHostToDevice, w->stream));
+  MMC_CUDA(launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream));
   MMC_CUDA(cudaStreamSynchronize(w->stream));
   w->header = h;
   return MMC_OK;

@@ -47,6 +47,11 @@
 
 // Slot state is touched once per kernel and handed to the next kernel through L2: loads and stores bypass L1
 // (ld.global.cg / st.global.cg), which stays with the cross-section and S(a,b) table gathers.
+// the S(a,b) kernel of worlds whose partitions are all expanded into dense tables (ce::DenseRows): no mode rows in
+// registers, so more, thinner threads to cover the L2 latency of the table gathers
+#ifndef MMC_EV_TSL_DENSE_THREADS
+#define MMC_EV_TSL_DENSE_THREADS 768
+#endif
 #ifndef MMC_STATE_CACHE_GLOBAL
 #define MMC_STATE_CACHE_GLOBAL 1
 #endif
@@ -65,6 +70,9 @@ namespace {
 constexpr int kFlightThreads = MMC_EV_FLIGHT_THREADS;
 constexpr int kWarpsPerBlock = kFlightThreads / 32;
 constexpr int kTslThreads = MMC_EV_TSL_THREADS;
+constexpr int kTslDenseThreads = MMC_EV_TSL_DENSE_THREADS;
+// kinds of the S(a,b) kernel: where a reconstruction reads from
+enum : int { kTslRowsGlobalSc = 0, kTslRowsSharedSc = 1, kTslDense = 2 };
 constexpr size_t kTslRowBytes = MMC_EV_TSL_ROWS_IN_REGS ? 0 : 10 * kTslThreads * sizeof(double2);
 
 // exclusive prefix of this warp among the CTA's warp totals, and the CTA total
@@ -447,14 +455,16 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
 //       44 KB at the reference's table shapes; rows are 80 bytes apart, i.e. 5 sixteen-byte bank groups -- odd -- so
 //       rows that differ modulo 8 never conflict).
 // Warps claim chunks of 32 queue entries from a counter; state loads and stores are coalesced over the compacted queue.
-template <bool kSharedSc>
-__global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
+template <int kKind>
+__global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslThreads, 1) event_tsl_kernel(
     const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
     const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
     const __grid_constant__ BoundaryArgs args, unsigned long long* counter_replicas) {
+  constexpr bool kSharedSc = kKind == kTslRowsSharedSc;
+  constexpr uint32_t kThreads = kKind == kTslDense ? kTslDenseThreads : kTslThreads;
   extern __shared__ __align__(16) char smem[];
   [[maybe_unused]] double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
-  char* s_sc = smem + kTslRowBytes;
+  [[maybe_unused]] char* s_sc = smem + kTslRowBytes;
   const uint32_t parity = pass & 1u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     q.count[parity] = 0;             // the alive queue this pass consumed: the next pass appends to it
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     q.count[5u + (parity ^ 1u)] = 0; // the boundary queue of the next pass
   }
   const uint32_t n = q.count[2u + parity];
-  constexpr uint32_t kWarps = kTslThreads / 32;
+  constexpr uint32_t kWarps = kThreads / 32;
 #if !MMC_EV_MERGE_BOUNDARY
   if (blockIdx.x * kWarps * 32u >= n) return;  // CTA-uniform: not even the first warp has work
 #endif
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
   if (kSharedSc) {
     const uint4* src = reinterpret_cast<const uint4*>(world_g + w.h->off_sc_arena);
     uint4* dst = reinterpret_cast<uint4*>(s_sc);
-    for (uint32_t k = threadIdx.x; k < w.h->sc_arena_bytes / 16; k += kTslThreads) dst[k] = __ldg(src + k);
+    for (uint32_t k = threadIdx.x; k < w.h->sc_arena_bytes / 16; k += kThreads) dst[k] = __ldg(src + k);
     __syncthreads();
   }
   const uint32_t lane = threadIdx.x & 31u;
@@ -489,11 +499,15 @@ __global__ void __launch_bounds__(kTslThreads, 1) event_tsl_kernel(
     }
   }
 #endif
+  auto make_rows = [&]() {
+    if constexpr (kKind == kTslDense) return ce::DenseRows{};
 #if MMC_EV_TSL_ROWS_IN_REGS
-  ce::RegisterRows<kSharedSc> rows(s_sc, w.h->off_sc_arena);
+    else return ce::RegisterRows<kSharedSc>(s_sc, w.h->off_sc_arena);
 #else
-  ce::SharedRows<kTslThreads, kSharedSc> rows(s_rows, s_sc, w.h->off_sc_arena);
+    else return ce::SharedRows<kTslThreads, kSharedSc>(s_rows, s_sc, w.h->off_sc_arena);
 #endif
+  };
+  auto rows = make_rows();
   // warps claim chunks of 32 queue entries from one counter: a scatter takes 10-30 rounds of reconstructions, so a
   // static split leaves the unlucky warps running alone at the end of every pass (chunks of 64: no faster)
   while (true) {
@@ -577,14 +591,16 @@ cudaError_t launch_event_pass(
 #endif
   if (marks) cudaEventRecord(marks[1], stream);
   // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queues can feed
-  const uint32_t per_cta = kTslThreads;
+  const uint32_t per_cta = header.tsl_all_dense ? kTslDenseThreads : kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
   if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
-  if (tsl.shared_sc)
-    event_tsl_kernel<true><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(
+  if (header.tsl_all_dense)
+    event_tsl_kernel<kTslDense><<<tsl_blocks, kTslDenseThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+  else if (tsl.shared_sc)
+    event_tsl_kernel<kTslRowsSharedSc><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(
         world_d, header, run, st, q, pass, args, counter_replicas);
   else
-    event_tsl_kernel<false><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+    event_tsl_kernel<kTslRowsGlobalSc><<<tsl_blocks, kTslThreads, kTslRowBytes, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
   return cudaGetLastError();
 }
 
@@ -594,9 +610,9 @@ cudaError_t configure_event_tsl(uint32_t sc_arena_bytes, size_t smem_optin, uint
   out.sm_count = sm_count;
   out.sc_arena_bytes = sc_arena_bytes;
   out.shared_sc = sc_arena_bytes > 0 && kTslRowBytes + sc_arena_bytes <= smem_optin;
-  cudaError_t e = cudaFuncSetAttribute(event_tsl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTslRowBytes));
+  cudaError_t e = cudaFuncSetAttribute(event_tsl_kernel<kTslRowsGlobalSc>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTslRowBytes));
   if (e == cudaSuccess && out.shared_sc)
-    e = cudaFuncSetAttribute(event_tsl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(event_tsl_kernel<kTslRowsSharedSc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kTslRowBytes + sc_arena_bytes));
   return e;
 }

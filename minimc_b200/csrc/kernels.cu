@@ -540,6 +540,32 @@ __global__ void resample_bank_kernel(
   next[t] = s;
 }
 
+// One thread per element of a dense table: the rank-R sum in the reference's order (0.0 + p0, + p1, ...), the same
+// IEEE operations as ce::pod_evaluate / ce::evaluate_inelastic make on the fly, so that a table entry IS the value
+// the on-the-fly path computes.
+__global__ void expand_dense_kernel(char* world, const DenseJob job) {
+  const uint64_t n = static_cast<uint64_t>(job.n_grid) * job.n_cdf * job.n_T;
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = static_cast<uint32_t>(i % job.n_T);
+  const uint32_t c = static_cast<uint32_t>((i / job.n_T) % job.n_cdf);
+  const uint32_t g = static_cast<uint32_t>(i / (static_cast<uint64_t>(job.n_T) * job.n_cdf));
+  const double* a = reinterpret_cast<const double*>(world + job.off_a) + static_cast<size_t>(c) * job.rank;
+  const double* m = reinterpret_cast<const double*>(world + job.off_m) + (static_cast<size_t>(g) * job.n_T + t) * job.rank;
+  double sum = 0;
+  for (uint32_t r = 0; r < job.rank; r++) sum = __dadd_rn(sum, __dmul_rn(a[r], m[r]));
+  reinterpret_cast<double*>(world + job.off_out)[i] = sum;
+}
+
+cudaError_t launch_expand_dense(char* world_d, const DenseJob* jobs, size_t n_jobs, cudaStream_t stream) {
+  for (size_t k = 0; k < n_jobs; k++) {
+    const uint64_t n = static_cast<uint64_t>(jobs[k].n_grid) * jobs[k].n_cdf * jobs[k].n_T;
+    if (n == 0) continue;
+    expand_dense_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(world_d, jobs[k]);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream) {
   if (run.n_histories == 0) return cudaSuccess;
   source_bank_kernel<<<static_cast<unsigned>((run.n_histories + 255) / 256), 256, 0, stream>>>(run, bank);

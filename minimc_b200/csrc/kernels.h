@@ -25,6 +25,9 @@ struct GenerationIO {
   unsigned long long* child_start = nullptr; // [n_histories] where that particle's run starts in `out`
 };
 
+// fills the dense reconstruction tables of the device-only tail of the image (world_blob.h DenseJob)
+cudaError_t launch_expand_dense(char* world_d, const DenseJob* jobs, size_t n_jobs, cudaStream_t stream);
+
 cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream);
 uint32_t bank_scan_blocks(uint64_t n_parents);
 cudaError_t launch_order_bank(

@@ -60,7 +60,8 @@ struct SurfaceRecord {
 struct WorldHeader {
   uint32_t total_bytes;
   int32_t n_surfaces, n_cells, n_materials, n_nuclides, n_groups;
-  int32_t pad0;
+  // 1 when every S(a,b) partition of the world has its dense reconstruction table (TslPartition::off_dense)
+  int32_t tsl_all_dense;
   // byte offsets from the start of the blob
   uint32_t off_surface_type;    // int32[n_surfaces]
   uint32_t off_surface_param;   // double[n_surfaces][4]
@@ -84,6 +85,10 @@ struct WorldHeader {
   // every partition's S[r] * CDF_modes[cdf][r] array (TslPartition::off_scaled_cdf_modes), contiguous: the S(a,b)
   // kernel of the event-split schedule stages this arena into shared memory when it fits
   uint32_t off_sc_arena, sc_arena_bytes;
+  // device-only tail of the image, [total_bytes, total_bytes + dense_bytes): the dense reconstruction tables, filled
+  // on the device after every upload (kernels.cu expand_dense_kernel); never part of the host image
+  uint32_t dense_bytes;
+  uint32_t pad1;
 };
 
 // ---- continuous-energy tables (blob offsets; see include/minimc_b200.h mmc_ce_desc)
@@ -117,7 +122,11 @@ struct TslPartition {
   uint32_t off_modes;      // double[n_grid][n_T][rank]
   uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
   uint32_t off_T_hint;     // SearchHint of T, 0 = none
-  uint32_t pad;
+  // double[n_grid][n_cdf][n_T]: the rank-R sums  sum_r S[r] * CDF_modes[cdf][r] * modes[grid][T][r]  of Evaluate
+  // (ThermalScattering.cpp:199-204,241-246) for EVERY (grid point, CDF node, temperature node), each summed in the
+  // reference's order -- the POD factors expanded once per upload, so that a reconstruction is two adjacent loads
+  // (T_lo, T_hi) and the reference's interpolation in T.  0 = not expanded (over the budget): sum on the fly.
+  uint32_t off_dense;
 };
 
 // ThermalScattering
@@ -131,7 +140,7 @@ struct TslTable {
   uint32_t n_betas, off_betas;  // concatenated betas of the alpha partitions (ThermalScattering::betas)
   uint32_t off_betas_hint;      // SearchHints of E / Es / betas: off_E_hint, off_Es_hint, off_betas_hint
   uint32_t off_T_hint;          // SearchHint of T
-  uint32_t pad_hint;
+  uint32_t off_xs_dense;        // double[n_E][n_T]: EvaluateInelastic at every (E, T) node, expanded like off_dense; 0 = none
   double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
 };
 
@@ -177,6 +186,15 @@ struct RunSpec {
   SensitivitySpec sensitivities[kMaxSensitivities];
   uint32_t sens_pending_capacity;  // per-history (bin, sum) entries of the sensitivity proxies
   uint32_t pad_sens;
+};
+
+// One expansion of POD factors into a dense table (device-side, after every upload of the image):
+// out[(g * n_cdf + c) * n_T + t] = sum_r a[c * rank + r] * m[(g * n_T + t) * rank + r], r ascending from 0.0.
+struct DenseJob {
+  uint32_t off_a;    // double[n_cdf][rank]: S[r] * CDF_modes[cdf][r]  (or S[r] * scatter_xs_E[E][r])
+  uint32_t off_m;    // double[n_grid][n_T][rank]
+  uint32_t off_out;  // double[n_grid][n_cdf][n_T], in the device-only tail
+  uint32_t n_grid, n_cdf, n_T, rank;
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.
