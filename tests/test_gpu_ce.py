@@ -155,6 +155,38 @@ def test_ce_schedules_agree_at_scale(tmp_path):
             assert c == results[0][2]
 
 
+def test_ce_dense_tables_change_nothing(tmp_path, monkeypatch):
+    """The dense reconstruction tables (world_blob.h TslPartition::off_dense, expanded on the device after every upload)
+    against the on-the-fly rank-R sums they replace: full-shape tables, 2*10^5 histories of single_zone and of
+    continuous_temperature with every partition expanded (default), with none (MMC_TSL_DENSE_MB=0) and with a budget
+    that only fits the small partitions (1 MB: expanded and summed rows mix inside one sampler) -- identical
+    tallies, counters and event traces, under the event-split and the fused schedule."""
+    ce_decks.generate_tables(tmp_path, "full")
+    n = 200_000
+    for text in (ce_decks.single_zone_benchmark_deck(tmp_path, histories=n, threads=4),
+                 ce_decks.continuous_temperature_deck(tmp_path, histories=n, threads=4)):
+        results = []
+        for budget in (None, "0", "1"):
+            if budget is None:
+                monkeypatch.delenv("MMC_TSL_DENSE_MB", raising=False)
+            else:
+                monkeypatch.setenv("MMC_TSL_DENSE_MB", budget)
+            for schedule in (capi.SCHEDULE_EVENT, capi.SCHEDULE_FUSED):
+                drv = capi.Driver(text=text)  # the budget is read when the device world is built
+                drv.set_options(schedule=schedule)
+                scores, squares = drv.solve()
+                c = drv.counters()
+                assert c["n_histories"] == n and c["n_lost"] == c["n_physics_errors"] == 0
+                records = [(int(r.history), int(r.event), int(r.rng_state), float(r.energy), tuple(r.position), tuple(r.direction))
+                           for r in capi.Driver(text=text).trace(0, 40, cap=1 << 16)]  # (the trace kernel has its own schedule)
+                results.append((scores, squares, c, records))
+        monkeypatch.delenv("MMC_TSL_DENSE_MB", raising=False)
+        for scores, squares, c, records in results[1:]:
+            assert np.array_equal(scores, results[0][0]) and np.array_equal(squares, results[0][1])
+            assert c == results[0][2]
+            assert records == results[0][3]
+
+
 def test_ce_lost_particles_are_counted_alike_by_every_schedule(tables):
     """A slab whose far void is missing (crossing the right plane finds no Cell) and, second, a source outside every
     Cell: World::FindCellContaining throws in the reference; here the run reports MMC_ERR_LOST_PARTICLE and the
