@@ -262,7 +262,11 @@ size_t mmc_last_error(char* buf, size_t cap);
 int mmc_device_count(void);
 
 /* Validates and uploads the tables (replaces nothing in the reference: this is
- * the one-off flattening of `const World`, World.cpp:20-24). */
+ * the one-off flattening of `const World`, World.cpp:20-24).  After the upload (and after every mmc_world_update)
+ * the device expands the POD factors of each thermal-scattering partition into a dense table of the sums
+ * BetaPartition::Evaluate / AlphaPartition::Evaluate make (ThermalScattering.cpp:199-204,241-246; same order, same
+ * values), up to 512 MB of device memory in all; the environment variable MMC_TSL_DENSE_MB changes that budget
+ * (0: never expand, every reconstruction sums its rank-R terms on the fly).  Results do not depend on it. */
 int mmc_world_create(const mmc_world_desc* desc, int device, mmc_world** out);
 void mmc_world_destroy(mmc_world* world);
 /* Uploads new table VALUES into an existing world (same shapes: the device image must have the same size), through
