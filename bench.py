@@ -152,8 +152,9 @@ ROOFLINE_NOTE = {
              "whole pass loop of one step (flight, boundary and S(a,b) kernel per event, kernel_split has their CUDA-event "
              "times and counts); particle state really streams through HBM here (traffic = ncu DRAM bytes). The "
              "dominant S(a,b) kernel is not HBM-bound: its first version sat at 88 % of peak L1 wavefronts (per-lane "
-             "table gathers); with the gathered rows in registers / shared memory it runs at 53 % of peak wavefronts "
-             "and 46 % of issue slots with 16 register-limited warps per SM: see DESIGN.md s4.1, s7 and profiles/",
+             "table gathers); with the POD factors expanded into dense tables on the device (two adjacent loads per "
+             "reconstruction, L2-resident) it runs 24 warps per SM at 43 % of issue slots, the stalls led by the L2 "
+             "latency of the table gathers: see DESIGN.md s3, s4.1, s7 and profiles/",
 }
 
 
