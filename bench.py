@@ -44,15 +44,15 @@ WORKLOADS = {
         "name": "single_zone (BASELINE configs[1], benchmarks/single_zone.xml as shipped): CE + S(a,b) H-in-H2O slab "
                 "5 cm at 450 K, surface tracking, 10403-bin current estimator, synthetic full-shape tables (rank 10, "
                 "partitions up to 97x18x294)",
-        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+        "histories_per_gpu": 1 << 25, "cpu_rate_guess": 4.0e4},
     "continuous_temperature": {
         "name": "continuous_temperature (BASELINE configs[4]): CE + S(a,b) slab, cell delta tracking, linear T(x) "
                 "300..600 K, synthetic full-shape tables",
-        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+        "histories_per_gpu": 1 << 25, "cpu_rate_guess": 4.0e4},
     "multi_zone": {
         "name": "multi_zone (BASELINE configs[2], benchmarks/multi_zone.xml): CE + S(a,b), 13 slab segments at "
                 "300..600 K between 14 planes, surface tracking, 202-bin current estimator, synthetic full-shape tables",
-        "histories_per_gpu": 1 << 23, "cpu_rate_guess": 4.0e4},
+        "histories_per_gpu": 1 << 25, "cpu_rate_guess": 4.0e4},
     "broomstick": {
         "name": "broomstick (BASELINE configs[3], benchmarks/broomstick.xml): CE + S(a,b), cylinder r = 1e-6 along x, "
                 "at most one collision per history, 184 x 239 cosine x energy bins, synthetic full-shape tables",
