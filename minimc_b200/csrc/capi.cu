@@ -514,8 +514,11 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     return e;
   };
   int status = MMC_OK;
+  unsigned long long claimed = 0;  // histories started so far, as of the last read
   while (alive && status == MMC_OK) {
-    const int batch = 8;
+    // passes between two reads of the queue lengths (a stream synchronisation: the GPU idles for a launch latency).
+    // While more than two refills of every slot are still unstarted nothing can end, so the reads are rarer.
+    const int batch = claimed + 2ull * p.event_slots < p.run.n_histories ? 32 : 8;
     for (int k = 0; k < batch && status == MMC_OK; k++, pass++) {
       cudaEvent_t inner[2] = {nullptr, nullptr};
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
@@ -533,7 +536,6 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     if (err == cudaSuccess) err = cudaStreamSynchronize(p.stream);
     if (err != cudaSuccess && status == MMC_OK) status = fail(MMC_ERR_CUDA, "event-split pass loop: %s", cudaGetErrorString(err));
     alive = w->h_event_counts[pass & 1u];
-    unsigned long long claimed = 0;
     std::memcpy(&claimed, w->h_event_counts + 4, sizeof(claimed));
     if (status == MMC_OK && alive && alive <= p.event_handover && claimed >= p.run.n_histories) {
       // The drain: every history has started and few are still alive.  A pass now costs its two launches' latency,
