@@ -187,6 +187,21 @@ def test_ce_dense_tables_change_nothing(tmp_path, monkeypatch):
             assert records == results[0][3]
 
 
+def test_ce_refresh_device_expands_the_dense_tables_again(tables):
+    """mmc_world_update on a continuous-energy world: the image is uploaded into the existing device world and the dense
+    reconstruction tables behind it are expanded again; solving after each refresh reproduces the golden .out."""
+    name, tag = "single_zone", "surface"
+    drv = capi.Driver(text=_case(tables, name, tag))
+    drv.set_options(secondary_capacity=256)
+    golden = (util.GOLDEN / "ce" / f"{name}__{tag}.out").read_text()
+    drv.solve()
+    assert drv.output() == golden
+    for _ in range(2):
+        drv.refresh_device()
+        drv.solve()
+        assert drv.output() == golden
+
+
 def test_ce_lost_particles_are_counted_alike_by_every_schedule(tables):
     """A slab whose far void is missing (crossing the right plane finds no Cell) and, second, a source outside every
     Cell: World::FindCellContaining throws in the reference; here the run reports MMC_ERR_LOST_PARTICLE and the
