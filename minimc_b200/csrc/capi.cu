@@ -813,7 +813,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
         o.off_dense = 0;
         if (reserve_dense(q.n_grid * q.n_cdf * q.n_temperature, tail[i])) {
           expanded[i] = 1;
-          jobs.push_back(DenseJob{o.off_scaled_cdf_modes, o.off_modes, tail[i], o.n_grid, o.n_cdf, o.n_T, o.rank});
+          jobs.push_back(DenseJob{o.off_scaled_cdf_modes, o.off_modes, tail[i], o.n_grid, o.n_cdf, o.n_T, o.rank, 1u});
         }
       }
       const uint32_t at = b.add(out.data(), out.size());
@@ -872,7 +872,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           tt.cutoff_energy = t.energy[t.n_energy - 1];  // ThermalScattering.hpp:125-126
           uint32_t xs_tail = 0;
           const bool xs_expanded = reserve_dense(t.n_energy * t.n_temperature, xs_tail);
-          if (xs_expanded) jobs.push_back(DenseJob{tt.off_xs_SE, tt.off_xs_T, xs_tail, 1u, tt.n_E, tt.n_T, tt.rank});
+          if (xs_expanded) jobs.push_back(DenseJob{tt.off_xs_SE, tt.off_xs_T, xs_tail, 1u, tt.n_E, tt.n_T, tt.rank, 0u});
           xr.off_tsl = b.add(&tt, 1);
           if (xs_expanded) dense_patches.push_back({xr.off_tsl + offsetof(TslTable, off_xs_dense), xs_tail});
         }

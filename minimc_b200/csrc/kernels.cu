@@ -554,7 +554,8 @@ __global__ void expand_dense_kernel(char* world, const DenseJob job) {
   const double* m = reinterpret_cast<const double*>(world + job.off_m) + (static_cast<size_t>(g) * job.n_T + t) * job.rank;
   double sum = 0;
   for (uint32_t r = 0; r < job.rank; r++) sum = __dadd_rn(sum, __dmul_rn(a[r], m[r]));
-  reinterpret_cast<double*>(world + job.off_out)[i] = sum;
+  const uint64_t at = job.cdf_fastest ? (static_cast<uint64_t>(g) * job.n_T + t) * job.n_cdf + c : i;
+  reinterpret_cast<double*>(world + job.off_out)[at] = sum;
 }
 
 cudaError_t launch_expand_dense(char* world_d, const DenseJob* jobs, size_t n_jobs, cudaStream_t stream) {

@@ -122,10 +122,12 @@ struct TslPartition {
   uint32_t off_modes;      // double[n_grid][n_T][rank]
   uint32_t grid_begin;     // index of this partition's first grid point in the concatenated Es / betas
   uint32_t off_T_hint;     // SearchHint of T, 0 = none
-  // double[n_grid][n_cdf][n_T]: the rank-R sums  sum_r S[r] * CDF_modes[cdf][r] * modes[grid][T][r]  of Evaluate
+  // double[n_grid][n_T][n_cdf]: the rank-R sums  sum_r S[r] * CDF_modes[cdf][r] * modes[grid][T][r]  of Evaluate
   // (ThermalScattering.cpp:199-204,241-246) for EVERY (grid point, CDF node, temperature node), each summed in the
-  // reference's order -- the POD factors expanded once per upload, so that a reconstruction is two adjacent loads
-  // (T_lo, T_hi) and the reference's interpolation in T.  0 = not expanded (over the budget): sum on the fly.
+  // reference's order -- the POD factors expanded once per upload, so that a reconstruction is two loads (T_lo, T_hi)
+  // and the reference's interpolation in T.  The CDF node is the fastest axis: the last four probes of find_cdf's
+  // bisections, and both ends of a try's bracket, fall into one 128-byte line per temperature row.
+  // 0 = not expanded (over the budget): sum on the fly.
   uint32_t off_dense;
 };
 
@@ -193,8 +195,9 @@ struct RunSpec {
 struct DenseJob {
   uint32_t off_a;    // double[n_cdf][rank]: S[r] * CDF_modes[cdf][r]  (or S[r] * scatter_xs_E[E][r])
   uint32_t off_m;    // double[n_grid][n_T][rank]
-  uint32_t off_out;  // double[n_grid][n_cdf][n_T], in the device-only tail
+  uint32_t off_out;  // double[n_grid][n_cdf][n_T] or, cdf_fastest, double[n_grid][n_T][n_cdf]; in the device-only tail
   uint32_t n_grid, n_cdf, n_T, rank;
+  uint32_t cdf_fastest;
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.
