@@ -27,6 +27,10 @@ namespace {
 // histories in flight in the event-split schedule.  Measured on B200, single_zone, 2^23 histories: 2^18 slots 4.4e7,
 // 2^20 8.06e7, 2^21 7.99e7, 2^22 7.5e7 hist/s (fewer slots: more, smaller passes; more slots: a longer drain tail)
 constexpr uint32_t kDefaultEventSlots = 1u << 20;
+// batches of 2^24 histories and more (r01j, dense tables, 2^25 histories: 2^19 slots 1.318e8, 2^20 1.387e8,
+// 1.5 * 2^20 1.407e8, 2^21 1.419e8, 2^22 1.397e8 hist/s): the longer drain tail of more slots is amortised
+constexpr uint32_t kLargeBatchEventSlots = 1u << 21;
+constexpr uint64_t kLargeBatchHistories = 1ull << 24;
 // live histories at or below which the drain of an event-split run is handed to the fused kernel
 constexpr uint32_t kDefaultEventHandover = 1u << 15;
 
@@ -441,7 +445,7 @@ int prepare_run(
     return fail(MMC_ERR_INVALID, "MMC_SCHEDULE_EVENT is for continuous-energy fixed-source runs");
   out.event_schedule = continuous_energy && !generation && !trace && schedule != MMC_SCHEDULE_FUSED;
   if (out.event_schedule) {
-    if (slots == 0) slots = kDefaultEventSlots;
+    if (slots == 0) slots = n_histories >= kLargeBatchHistories ? kLargeBatchEventSlots : kDefaultEventSlots;
     // worlds with fission keep a secondary deque per slot: bound its memory
     if (w->has_fission) slots = std::min<uint32_t>(slots, 1u << 18);
     out.event_slots = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(n_histories, 1), slots));
