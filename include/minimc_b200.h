@@ -227,7 +227,11 @@ typedef struct mmc_event_record {
   uint64_t rng_state;               /* minstd_rand state after the event */
 } mmc_event_record;
 
-typedef struct mmc_world mmc_world; /* opaque: owns the device copy of the tables */
+/* opaque: owns the device copy of the tables and the scratch of a run.  ONE run at a time per world: concurrent
+ * calls from several host threads serialise on the world; the asynchronous device-buffer entry points
+ * (mmc_fixed_source_run_device, mmc_generation_run, ...) must be given the same stream for as long as work of an
+ * earlier call may still be in flight -- two streams on one world would race on that scratch. */
+typedef struct mmc_world mmc_world;
 
 /* How the histories of a fixed-source run are scheduled on the device (results are identical either way).
  * FUSED: one persistent kernel, a particle stays in registers from birth to death (multigroup worlds always).
@@ -243,10 +247,11 @@ typedef enum mmc_schedule {
 /* Optional knobs; zero-initialise for defaults. */
 typedef struct mmc_run_options {
   uint32_t struct_size;             /* sizeof(mmc_run_options) */
-  int32_t device;                   /* CUDA device ordinal; -1 = current */
+  int32_t device;                   /* used by the host layer's Driver (which device its world is created on); the
+                                     * mmc_world entry points run on the device the world was created on */
   int32_t tracking;                 /* mmc_tracking */
   int32_t rng_mode;                 /* mmc_rng_mode */
-  uint32_t secondary_capacity;      /* per-history fission queue slots (default 64) */
+  uint32_t secondary_capacity;      /* per-history fission queue slots (default 32) */
   uint32_t pending_capacity;        /* per-history distinct scored bins (default 32) */
   uint32_t blocks_per_sm;           /* 0 = library default */
   uint32_t schedule;                /* mmc_schedule; 0 = library default */

@@ -412,6 +412,36 @@ def continuous_temperature_deck(table_dir, *, histories=1000, threads=1, seed=No
     return s
 
 
+def mixed_temperature_deck(table_dir, *, histories=1000, threads=1, seed=None, n_energy_bins=40) -> str:
+    """Three slab segments under cell delta tracking: the outer two carry their own constant temperature
+    (Cell::AssignTemperature, Cell.cpp:107-113: a ConstantField), the middle one falls back to the global linear field
+    of continuous_temperature.xml -- evaluated S(a,b) rows (one load) and two-row reconstructions (interpolated in T at
+    every call) inside one world."""
+    s = "<minimc>\n" + _general(histories, threads, seed, "cell delta")
+    s += "<nuclides>\n  <continuous>\n" + _hydrogen(table_dir, "623K", 623.6) + "  </continuous>\n</nuclides>\n"
+    s += '<materials>\n  <material name="hydrogen in water" aden="0.066854">\n    <nuclide name="hydrogen in water" afrac="1"/>\n  </material>\n</materials>\n'
+    s += ('<surfaces>\n  <planex name="plane-1" x="-1e-6"/>\n  <planex name="plane-2" x="1.4"/>\n'
+          '  <planex name="plane-3" x="3.0"/>\n  <planex name="plane-4" x="4.33"/>\n</surfaces>\n')
+    s += ('<cells>\n  <void>\n    <surface name="plane-1" sense="-1"/>\n  </void>\n'
+          '  <cell name="segment-1" material="hydrogen in water" temperature="350">\n'
+          '    <surface name="plane-1" sense="+1"/>\n    <surface name="plane-2" sense="-1"/>\n  </cell>\n'
+          '  <cell name="segment-2" material="hydrogen in water">\n'
+          '    <surface name="plane-2" sense="+1"/>\n    <surface name="plane-3" sense="-1"/>\n  </cell>\n'
+          '  <cell name="segment-3" material="hydrogen in water" temperature="525.5">\n'
+          '    <surface name="plane-3" sense="+1"/>\n    <surface name="plane-4" sense="-1"/>\n  </cell>\n'
+          '  <void>\n    <surface name="plane-4" sense="+1"/>\n  </void>\n</cells>\n')
+    s += _source(0.56e-6)
+    # A gentle gradient: a particle that grazes a plane (|dx| * nudge below half an ulp of the plane's x: the reference's
+    # absolute nudge, Constants.hpp:15, does not move it across) stays in its Cell while it wanders through its
+    # neighbours; with the 69.28 K/cm of continuous_temperature.xml T(x) then leaves the tables' temperature grid on
+    # the left and the reference's SampleBeta throws (std::terminate).  5 K/cm keeps T inside [273.6, 800] K for |x| < 29 cm.
+    s += ('<temperature>\n  <linear>\n    <bounds lower="300" upper="600"/>\n    <intercept b="420"/>\n'
+          '    <gradient x="5.0" y="0" z="0"/>\n  </linear>\n</temperature>\n')
+    bounds = energy_boundaries(n_energy_bins)
+    s += "<estimators>\n" + _current("leakage", "plane-4", bounds) + _current("reflected", "plane-1", bounds) + "</estimators>\n</minimc>\n"
+    return s
+
+
 def broomstick_deck(table_dir, *, histories=1000, threads=1, seed=None, temperature=450.0, n_energy_bins=24,
                     n_cosine_bins=12) -> str:
     """benchmarks/broomstick.xml: a cylinder of radius 1e-6 along x between two planes; a particle born on the axis
@@ -461,10 +491,19 @@ def free_gas_sphere_deck(table_dir, *, histories=1000, threads=1, seed=None, tra
     return s
 
 
+def thermal_fissile_sphere_deck(table_dir, **kw) -> str:
+    """free_gas_sphere_deck with a thermal (0.0253 eV) source in the fuel pellet: ContinuousFission::Interact
+    (ContinuousReaction.cpp:252-265) happens within the first histories, so the golden traces hold fission events and
+    banked secondaries (FixedSource.cpp:63-72)."""
+    kw.setdefault("energy", 2.53e-8)
+    return free_gas_sphere_deck(table_dir, **kw)
+
+
 CE_DECKS = {
     "single_zone": slab_deck,
     "multi_zone": multi_zone_deck,
     "continuous_temperature": continuous_temperature_deck,
     "broomstick": broomstick_deck,
     "free_gas_sphere": free_gas_sphere_deck,
+    "thermal_fissile_sphere": thermal_fissile_sphere_deck,
 }

@@ -126,6 +126,10 @@ void scratch_release(int device, ScratchKind kind, void* ptr, size_t bytes) {
 }  // namespace
 
 struct mmc_world {
+  // One run at a time per world: the run entry points share the world's scratch (history counter, pending and
+  // secondary tables, event-split state, tally mirrors).  A second host thread waits here; the asynchronous
+  // device-buffer entry points must additionally be given ONE stream per world (include/minimc_b200.h).
+  std::recursive_mutex run_mutex;
   int device = 0;
   char* d_blob = nullptr;
   char* h_blob = nullptr;  // pinned host copy of the image: the source of every upload
@@ -634,8 +638,9 @@ namespace {
 // `jobs`: the dense reconstruction tables to expand on the device after the image is uploaded (world_blob.h
 // DenseJob); their space is the device-only tail behind the image.
 int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& header_out, bool& has_fission_out,
-                     std::vector<DenseJob>& jobs) {
+                     std::vector<DenseJob>& jobs, std::vector<EvalJob>& eval_jobs) {
   jobs.clear();
+  eval_jobs.clear();
   // dense tables: offsets are known relative to the tail while the image is still growing; the fields that hold them
   // are patched once the image's size is final
   struct DensePatch { size_t field_at; uint32_t tail_offset; };
@@ -645,14 +650,18 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
   bool dense_complete = true;
   int dense_tables = 0;
   // reserves n doubles in the tail; false when over the budget
-  auto reserve_dense = [&](uint64_t n_doubles, uint32_t& tail_offset) {
+  auto reserve_tail = [&](uint64_t n_doubles, uint32_t& tail_offset) {
     const uint64_t bytes = (n_doubles * 8 + 15) & ~15ull;
-    if (n_doubles == 0 || dense_total + bytes > dense_budget) {
+    if (n_doubles == 0 || dense_total + bytes > dense_budget) return false;
+    tail_offset = static_cast<uint32_t>(dense_total);
+    dense_total += bytes;
+    return true;
+  };
+  auto reserve_dense = [&](uint64_t n_doubles, uint32_t& tail_offset) {
+    if (!reserve_tail(n_doubles, tail_offset)) {
       dense_complete = false;
       return false;
     }
-    tail_offset = static_cast<uint32_t>(dense_total);
-    dense_total += bytes;
     dense_tables++;
     return true;
   };
@@ -709,6 +718,25 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
   }
   h.off_cell_field_kind = b.add(field_kind.data(), field_kind.size());
   h.off_cell_field_param = b.add(field_param.data(), field_param.size());
+  // distinct constant temperatures of the material cells, in order of first appearance: the temperatures the S(a,b)
+  // partitions are evaluated at once per upload (TslPartition::off_eval)
+  std::vector<double> eval_T;
+  std::vector<int32_t> cell_eval_slot(d->n_cells, -1);
+  if (G == 0 && dense_budget > 0) {
+    for (int c = 0; c < d->n_cells; c++) {
+      if (d->cell_material[c] < 0 || field_kind[c] != MMC_FIELD_CONSTANT) continue;
+      const double T = field_param[static_cast<size_t>(c) * 6];
+      size_t k = 0;
+      while (k < eval_T.size() && std::memcmp(&eval_T[k], &T, sizeof(double)) != 0) k++;
+      if (k == eval_T.size()) {
+        if (eval_T.size() == static_cast<size_t>(kMaxEvalT)) continue;
+        eval_T.push_back(T);
+      }
+      cell_eval_slot[c] = static_cast<int32_t>(k);
+    }
+  }
+  h.off_cell_eval_slot = b.add(cell_eval_slot.data(), cell_eval_slot.size());
+  h.n_eval_T = static_cast<int32_t>(eval_T.size());
   const int32_t zero_begin[1] = {0};
   h.off_mat_aden = b.add(d->material_aden, d->n_materials);
   h.off_mat_nuc_begin = d->n_materials ? b.add(d->material_nuclide_begin, d->n_materials + 1) : b.add(zero_begin, 1);
@@ -797,8 +825,8 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
     }
     auto partitions = [&](const mmc_tsl_partition* p, int n, std::vector<double>& concatenated) {
       std::vector<TslPartition> out(n);
-      std::vector<uint32_t> tail(n, 0);
-      std::vector<char> expanded(n, 0);
+      std::vector<uint32_t> tail(n, 0), tail_eval(n, 0);
+      std::vector<char> expanded(n, 0), evaluated(n, 0);
       for (int i = 0; i < n; i++) {
         const mmc_tsl_partition& q = p[i];
         TslPartition& o = out[i];
@@ -819,10 +847,35 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           expanded[i] = 1;
           jobs.push_back(DenseJob{o.off_scaled_cdf_modes, o.off_modes, tail[i], o.n_grid, o.n_cdf, o.n_T, o.rank, 1u});
         }
+        o.off_eval = 0;
+        if (!eval_T.empty() && q.n_temperature <= 255 &&
+            reserve_tail(eval_T.size() * q.n_grid * q.n_cdf, tail_eval[i])) {
+          evaluated[i] = 1;
+          EvalJob job{};
+          job.off_a = o.off_scaled_cdf_modes;
+          job.off_m = o.off_modes;
+          job.off_out = tail_eval[i];
+          job.n_grid = o.n_grid, job.n_cdf = o.n_cdf, job.n_T = o.n_T, job.rank = o.rank;
+          job.n_slots = static_cast<uint32_t>(eval_T.size());
+          for (size_t s = 0; s < eval_T.size(); s++) {
+            // "Find index of Temperature above and below target Temperature", ThermalScattering.cpp:188-196,230-238
+            const double* Ts = q.temperature;
+            const size_t candidate = static_cast<size_t>(std::upper_bound(Ts, Ts + q.n_temperature, eval_T[s]) - Ts);
+            const size_t T_hi_i = candidate == q.n_temperature ? candidate - 1 : candidate;
+            const size_t T_lo_i = T_hi_i == 0 ? T_hi_i : T_hi_i - 1;
+            job.t_hi[s] = static_cast<uint8_t>(T_hi_i);
+            job.t_lo[s] = static_cast<uint8_t>(T_lo_i);
+            job.dT[s] = Ts[T_hi_i] - Ts[T_lo_i];
+            job.tT[s] = eval_T[s] - Ts[T_lo_i];
+          }
+          eval_jobs.push_back(job);
+        }
       }
       const uint32_t at = b.add(out.data(), out.size());
-      for (int i = 0; i < n; i++)
+      for (int i = 0; i < n; i++) {
         if (expanded[i]) dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_dense), tail[i]});
+        if (evaluated[i]) dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_eval), tail_eval[i]});
+      }
       return at;
     };
     std::vector<CeNuclide> nuclides(d->n_nuclides);
@@ -894,6 +947,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
     std::memcpy(b.bytes.data() + patch.field_at, &absolute, sizeof(uint32_t));
   }
   for (DenseJob& job : jobs) job.off_out += h.total_bytes;
+  for (EvalJob& job : eval_jobs) job.off_out += h.total_bytes;
   b.header() = h;
   header_out = h;
   has_fission_out = has_fission;
@@ -913,7 +967,8 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   WorldHeader h{};
   bool has_fission = false;
   std::vector<DenseJob> dense_jobs;
-  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs)) return s;
+  std::vector<EvalJob> eval_jobs;
+  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs, eval_jobs)) return s;
 
   auto* w = new mmc_world;
   w->device = device;
@@ -929,6 +984,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   if (e == cudaSuccess) e = cudaMalloc(&w->d_next, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream);
+  if (e == cudaSuccess) e = launch_evaluate_rows(w->d_blob, eval_jobs.data(), eval_jobs.size(), w->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
   if (e != cudaSuccess) {
     mmc_world_destroy(w);
@@ -947,7 +1003,8 @@ int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
   WorldHeader h{};
   bool has_fission = false;
   std::vector<DenseJob> dense_jobs;
-  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs)) return s;
+  std::vector<EvalJob> eval_jobs;
+  if (int s = build_world_blob(d, b, h, has_fission, dense_jobs, eval_jobs)) return s;
   if (h.total_bytes != w->blob_bytes || h.dense_bytes != w->header.dense_bytes || has_fission != w->has_fission ||
       h.n_groups != w->header.n_groups)
     return fail(MMC_ERR_INVALID, "mmc_world_update: the new tables have a different shape (%u bytes, world holds %u): "
@@ -956,6 +1013,7 @@ int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
   std::memcpy(w->h_blob, b.bytes.data(), w->blob_bytes);
   MMC_CUDA(cudaMemcpyAsync(w->d_blob, w->h_blob, w->blob_bytes, cudaMemcpyHostToDevice, w->stream));
   MMC_CUDA(launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream));
+  MMC_CUDA(launch_evaluate_rows(w->d_blob, eval_jobs.data(), eval_jobs.size(), w->stream));
   MMC_CUDA(cudaStreamSynchronize(w->stream));
   w->header = h;
   return MMC_OK;
@@ -964,6 +1022,7 @@ int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
 void mmc_world_destroy(mmc_world* w) {
   if (!w) return;
   cudaSetDevice(w->device);
+  cudaDeviceSynchronize();  // work in flight (on any stream a caller passed) may still use the scratch parked below
   if (w->stream) cudaStreamDestroy(w->stream);
   cudaFree(w->d_blob);
   if (w->h_blob) cudaFreeHost(w->h_blob);
@@ -990,6 +1049,8 @@ int mmc_fixed_source_run_device(
     uint64_t seed0, uint64_t first_history, uint64_t n_histories, const mmc_run_options* options, uint64_t* d_scores,
     uint64_t* d_square_scores, mmc_counters* d_counters) {
   auto* w = const_cast<mmc_world*>(world);
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   Prepared p;
   if (int s = prepare_run(w, source, estimators, n_estimators, seed0, first_history, n_histories, options, false, p)) return s;
   if (!d_counters) return fail(MMC_ERR_INVALID, "d_counters is NULL");
@@ -1017,6 +1078,8 @@ static_assert(sizeof(mmc_site) == sizeof(BankSite), "mmc_site and BankSite must 
 int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_index,
                            uint64_t n, const mmc_run_options* options, mmc_site* d_bank) {
   auto* w = const_cast<mmc_world*>(world);
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   Prepared p;
   if (int s = prepare_run(w, source, nullptr, 0, seed0, first_index, n, options, true, p)) return s;
   if (n && !d_bank) return fail(MMC_ERR_INVALID, "d_bank is NULL");
@@ -1030,6 +1093,8 @@ int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64
                        const mmc_run_options* options, mmc_site* d_bank_out, uint64_t bank_capacity, uint64_t* d_n_out,
                        uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters) {
   auto* w = const_cast<mmc_world*>(world);
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
   // the source of a generation is the bank: a placeholder source satisfies prepare_run's checks
   mmc_source_desc placeholder{};
@@ -1116,10 +1181,12 @@ int mmc_fixed_source_run_sensitivities(
                                 scores, square_scores, counters);
   if (!world) return fail(MMC_ERR_INVALID, "world handle is NULL");
   auto* w = const_cast<mmc_world*>(world);
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   if (n_sensitivities < 0 || n_sensitivities > kMaxSensitivities)
     return fail(MMC_ERR_INVALID, "n_sensitivities %d out of range [0, %d]", n_sensitivities, kMaxSensitivities);
   if (!sensitivities || !sens_scores || !sens_square_scores)
     return fail(MMC_ERR_INVALID, "sensitivities / sens_scores / sens_square_scores is NULL");
+  if (n_estimators > 0 && (!scores || !square_scores)) return fail(MMC_ERR_INVALID, "scores / square_scores is NULL");
   mmc_run_options opt{};
   if (options) opt = *options;
   opt.struct_size = sizeof(mmc_run_options);
@@ -1226,6 +1293,7 @@ int mmc_fixed_source_run(
   cudaStream_t stream = opt.stream ? static_cast<cudaStream_t>(opt.stream) : world->stream;
   // [scores | square_scores | counters] in one device buffer with a pinned host mirror, both kept by the world
   auto* w = const_cast<mmc_world*>(world);
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   constexpr size_t kCounterWords = sizeof(mmc_counters) / sizeof(unsigned long long);
   const size_t words = 2 * total_bins + kCounterWords;
   if (words > w->tally_words) {
@@ -1262,6 +1330,8 @@ int mmc_trace_histories(
     const mmc_world* world, const mmc_source_desc* source, uint64_t seed0, uint64_t first_history, uint64_t n_histories,
     const mmc_run_options* options, mmc_event_record* records, size_t cap, size_t* n_records) {
   auto* w = const_cast<mmc_world*>(world);
+  if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
+  std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
   Prepared p;
   if (int s = prepare_run(w, source, nullptr, 0, seed0, first_history, n_histories, options, true, p)) return s;
   if (!records || !n_records) return fail(MMC_ERR_INVALID, "records / n_records is NULL");

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslTh
     const TslTable& t = *w.at<TslTable>(MMC_LD(st.tsl_off[slot]));
     bool error = false;
     double mu = 0, E_p = 0;
-    ce::tsl_sample(w, t, p.rng, p.energy, T, error, rows, mu, E_p);
+    ce::tsl_sample(w, t, p.rng, p.energy, T, ce::cell_eval_slot(w, MMC_LD(st.cell[slot])), error, rows, mu, E_p);
     if (!error) {
       // the direction is only needed now: it stays in memory while the sampler's state fills the registers
       p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);

@@ -567,6 +567,37 @@ cudaError_t launch_expand_dense(char* world_d, const DenseJob* jobs, size_t n_jo
   return cudaGetLastError();
 }
 
+// One thread per (temperature slot, grid point, CDF node): BetaPartition::Evaluate / AlphaPartition::Evaluate
+// (ThermalScattering.cpp:183-215,225-256) at the slot's temperature -- both rank-R sums in the reference's order from
+// 0.0 and the interpolation v_lo + (v_hi - v_lo) / (T_hi - T_lo) * (T - T_lo), the IEEE operations ce::pod_evaluate
+// makes on the fly (__ddiv_rn is the correctly rounded quotient ce::divide_by reproduces).
+__global__ void evaluate_rows_kernel(char* world, const __grid_constant__ EvalJob job) {
+  const uint32_t s = blockIdx.y;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= job.n_grid * job.n_cdf) return;
+  const uint32_t c = i % job.n_cdf, g = i / job.n_cdf;
+  const double* a = reinterpret_cast<const double*>(world + job.off_a) + static_cast<size_t>(c) * job.rank;
+  const double* m = reinterpret_cast<const double*>(world + job.off_m);
+  const double* hi = m + (static_cast<size_t>(g) * job.n_T + job.t_hi[s]) * job.rank;
+  const double* lo = m + (static_cast<size_t>(g) * job.n_T + job.t_lo[s]) * job.rank;
+  double v_hi = 0, v_lo = 0;
+  for (uint32_t r = 0; r < job.rank; r++) {
+    v_hi = __dadd_rn(v_hi, __dmul_rn(a[r], hi[r]));
+    v_lo = __dadd_rn(v_lo, __dmul_rn(a[r], lo[r]));
+  }
+  reinterpret_cast<double*>(world + job.off_out)[(static_cast<size_t>(s) * job.n_grid + g) * job.n_cdf + c] =
+      __dadd_rn(v_lo, __dmul_rn(__ddiv_rn(__dsub_rn(v_hi, v_lo), job.dT[s]), job.tT[s]));
+}
+
+cudaError_t launch_evaluate_rows(char* world_d, const EvalJob* jobs, size_t n_jobs, cudaStream_t stream) {
+  for (size_t k = 0; k < n_jobs; k++) {
+    const uint32_t n = jobs[k].n_grid * jobs[k].n_cdf;
+    if (n == 0 || jobs[k].n_slots == 0) continue;
+    evaluate_rows_kernel<<<dim3((n + 255) / 256, jobs[k].n_slots), 256, 0, stream>>>(world_d, jobs[k]);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream) {
   if (run.n_histories == 0) return cudaSuccess;
   source_bank_kernel<<<static_cast<unsigned>((run.n_histories + 255) / 256), 256, 0, stream>>>(run, bank);
@@ -690,6 +721,8 @@ cudaError_t launch_trace(
 int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, size_t smem, bool perturb) {
   return dispatch_history_kernel(tracking, continuous_energy, generation, perturb, [&](auto kernel) {
     int n = 0;
+    // the query answers 0 for dynamic shared memory above the function's current limit: opt in first
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreadsPerBlock, smem);
     return n;
   });

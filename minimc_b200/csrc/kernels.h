@@ -27,6 +27,8 @@ struct GenerationIO {
 
 // fills the dense reconstruction tables of the device-only tail of the image (world_blob.h DenseJob)
 cudaError_t launch_expand_dense(char* world_d, const DenseJob* jobs, size_t n_jobs, cudaStream_t stream);
+// fills the evaluated S(a,b) tables (world_blob.h EvalJob, TslPartition::off_eval)
+cudaError_t launch_evaluate_rows(char* world_d, const EvalJob* jobs, size_t n_jobs, cudaStream_t stream);
 
 cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t stream);
 uint32_t bank_scan_blocks(uint64_t n_parents);

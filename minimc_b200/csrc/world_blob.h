@@ -88,8 +88,15 @@ struct WorldHeader {
   // device-only tail of the image, [total_bytes, total_bytes + dense_bytes): the dense reconstruction tables, filled
   // on the device after every upload (kernels.cu expand_dense_kernel); never part of the host image
   uint32_t dense_bytes;
+  // int32[n_cells]: index of the cell's constant temperature among the world's evaluated temperatures
+  // (TslPartition::off_eval), -1 for void cells, cells with a linear temperature field and cells past kMaxEvalT
+  uint32_t off_cell_eval_slot;
+  int32_t n_eval_T;
   uint32_t pad1;
 };
+
+// distinct constant cell temperatures a world keeps evaluated S(a,b) tables for (BASELINE configs: 1, 13, 1, 0)
+constexpr int kMaxEvalT = 64;
 
 // ---- continuous-energy tables (blob offsets; see include/minimc_b200.h mmc_ce_desc)
 constexpr int kMaxCeReactions = 4;  // per nuclide: capture, scatter, fission (+1 spare)
@@ -129,6 +136,12 @@ struct TslPartition {
   // bisections, and both ends of a try's bracket, fall into one 128-byte line per temperature row.
   // 0 = not expanded (over the budget): sum on the fly.
   uint32_t off_dense;
+  // double[n_eval_T][n_grid][n_cdf]: Evaluate(cdf, grid, T_s) itself -- the two rank-R sums AND the interpolation in
+  // temperature (ThermalScattering.cpp:206-214,248-255, same operations in the same order) -- for every distinct
+  // constant cell temperature T_s of the world (WorldHeader::off_cell_eval_slot).  Evaluate is a pure function of
+  // (cdf, grid, T) and T is a per-cell constant in BASELINE configs[1], [2], [3]: a reconstruction there is ONE load
+  // and find_cdf's comparator probes one contiguous row of n_cdf doubles.  0 = none.
+  uint32_t off_eval;
 };
 
 // ThermalScattering
@@ -198,6 +211,18 @@ struct DenseJob {
   uint32_t off_out;  // double[n_grid][n_cdf][n_T] or, cdf_fastest, double[n_grid][n_T][n_cdf]; in the device-only tail
   uint32_t n_grid, n_cdf, n_T, rank;
   uint32_t cdf_fastest;
+};
+
+// Evaluate(cdf, grid, T_s) of one partition for every evaluated temperature (device-side, after every upload):
+// out[(s * n_grid + g) * n_cdf + c] = v_lo + (v_hi - v_lo) / dT[s] * tT[s] with
+// v_k = sum_r a[c * rank + r] * m[(g * n_T + t_k[s]) * rank + r], r ascending from 0.0.
+struct EvalJob {
+  uint32_t off_a;    // double[n_cdf][rank]: S[r] * CDF_modes[cdf][r]
+  uint32_t off_m;    // double[n_grid][n_T][rank]
+  uint32_t off_out;  // double[n_slots][n_grid][n_cdf], in the device-only tail
+  uint32_t n_grid, n_cdf, n_T, rank, n_slots;
+  uint8_t t_lo[kMaxEvalT], t_hi[kMaxEvalT];  // T_lo_i, T_hi_i of the partition's temperature axis for each T_s
+  double dT[kMaxEvalT], tT[kMaxEvalT];       // T_hi - T_lo, T_s - T_lo
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.

@@ -153,8 +153,12 @@ class KEigenvalue:
                     counts = [int(v) for v in torch.stack(gathered).cpu().flatten().tolist()]
                 else:
                     counts = [int(n_out.item())]
-                if counts[rank] > capacity:
-                    raise capi.MinimcError(capi.ERR_CAPACITY, "fission bank overflow: raise bank_capacity_factor")
+                # decided alike on every rank (each holds all counts): a rank-local check would leave the other
+                # ranks waiting in the exchange for a peer that has raised
+                for r in range(P):
+                    if counts[r] > int(self.bank_capacity_factor * max(shard(0, N, r, P)[1], 1)) + 1024:
+                        raise capi.MinimcError(capi.ERR_CAPACITY,
+                                               f"fission bank overflow on rank {r}: raise bank_capacity_factor")
                 M = sum(counts)
                 k_cycle.append(M / N)
                 bank_sizes.append(M)

@@ -121,7 +121,8 @@ CE_HISTORIES = 4000
 # decks whose every arithmetic step is restated bit for bit on the device; free_gas_sphere with surface tracking
 # reaches the free-gas cross-section adjustment (erf, exp: CUDA's, ulp-level differences) -- see physics_ce.cuh
 CE_EXACT = {("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
-            ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "delta")}
+            ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "delta"),
+            ("thermal_fissile_sphere", "delta")}
 
 
 def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
@@ -131,7 +132,7 @@ def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
     for name, fn in ce_decks.CE_DECKS.items():
         for tag, tracking in TRACKING.items():
             kw = {"histories": histories, "threads": 4, "seed": seed}
-            if name in ("single_zone", "free_gas_sphere"):
+            if name in ("single_zone", "free_gas_sphere", "thermal_fissile_sphere"):
                 kw["tracking"] = tracking
             elif name == "multi_zone":
                 kw["tracking"] = tracking or "surface"
@@ -146,7 +147,7 @@ def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
 
 CE_CASE_IDS = [("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
                ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "surface"),
-               ("free_gas_sphere", "delta")]
+               ("free_gas_sphere", "delta"), ("thermal_fissile_sphere", "surface"), ("thermal_fissile_sphere", "delta")]
 
 
 # ---------------------------------------------------------------- sensitivities
