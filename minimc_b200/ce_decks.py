@@ -464,7 +464,8 @@ def broomstick_deck(table_dir, *, histories=1000, threads=1, seed=None, temperat
     return s
 
 
-def free_gas_sphere_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking=None, energy=1.0e-3) -> str:
+def free_gas_sphere_deck(table_dir, *, histories=1000, threads=1, seed=None, tracking=None, energy=1.0e-3,
+                         pellet_temperature=900) -> str:
     """A test/continuous.xml-like problem without thermal scattering data: concentric spheres of hydrogen (free gas
     always, awr < 1), an oxygen-like scatterer (free gas only below 500 kT / awr) and a fissile heavy nuclide
     (ContinuousFission with a nubar table), isotropic source.  Cell temperatures above and below T_eval exercise both
@@ -481,7 +482,7 @@ def free_gas_sphere_deck(table_dir, *, histories=1000, threads=1, seed=None, tra
           '    <nuclide name="oxygen" afrac="0.8"/>\n  </material>\n</materials>\n')
     s += ('<surfaces>\n  <sphere name="pellet">\n    <center x="0" y="0" z="0"/>\n    <radius r="1.5"/>\n  </sphere>\n'
           '  <sphere name="moderator">\n    <center x="0" y="0" z="0"/>\n    <radius r="6"/>\n  </sphere>\n</surfaces>\n')
-    s += ('<cells>\n  <cell name="pellet" material="fuel" temperature="900">\n    <surface name="pellet" sense="-1"/>\n  </cell>\n'
+    s += (f'<cells>\n  <cell name="pellet" material="fuel" temperature="{pellet_temperature}">\n    <surface name="pellet" sense="-1"/>\n  </cell>\n'
           '  <cell name="moderator" material="water" temperature="280">\n    <surface name="pellet" sense="+1"/>\n'
           '    <surface name="moderator" sense="-1"/>\n  </cell>\n'
           '  <void>\n    <surface name="moderator" sense="+1"/>\n  </void>\n</cells>\n')
@@ -494,8 +495,11 @@ def free_gas_sphere_deck(table_dir, *, histories=1000, threads=1, seed=None, tra
 def thermal_fissile_sphere_deck(table_dir, **kw) -> str:
     """free_gas_sphere_deck with a thermal (0.0253 eV) source in the fuel pellet: ContinuousFission::Interact
     (ContinuousReaction.cpp:252-265) happens within the first histories, so the golden traces hold fission events and
-    banked secondaries (FixedSource.cpp:63-72)."""
+    banked secondaries (FixedSource.cpp:63-72).  Both cells are colder than 1.01 x the evaluations' 293.6 K, so
+    ContinuousEvaluation::IsValid holds (Q5) and no cross section takes the erf/exp free-gas adjustment
+    (ContinuousReaction.cpp:225-238): the deck is bit-exact under both tracking modes, free-gas scatters included."""
     kw.setdefault("energy", 2.53e-8)
+    kw.setdefault("pellet_temperature", 290)
     return free_gas_sphere_deck(table_dir, **kw)
 
 

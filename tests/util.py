@@ -122,7 +122,7 @@ CE_HISTORIES = 4000
 # reaches the free-gas cross-section adjustment (erf, exp: CUDA's, ulp-level differences) -- see physics_ce.cuh
 CE_EXACT = {("single_zone", "surface"), ("single_zone", "delta"), ("multi_zone", "surface"), ("multi_zone", "delta"),
             ("continuous_temperature", "delta"), ("broomstick", "surface"), ("free_gas_sphere", "delta"),
-            ("thermal_fissile_sphere", "delta")}
+            ("thermal_fissile_sphere", "surface"), ("thermal_fissile_sphere", "delta")}
 
 
 def ce_cases(table_dir, histories=CE_HISTORIES, seed=None):
