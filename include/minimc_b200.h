@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMC_ABI_VERSION 1
+#define MMC_ABI_VERSION 2
 
 typedef enum mmc_status {
   MMC_OK = 0,
@@ -359,7 +359,13 @@ int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source
 int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64_t n_in,
                        const mmc_estimator_desc* estimators, int32_t n_estimators, int32_t score,
                        const mmc_run_options* options, mmc_site* d_bank_out, uint64_t bank_capacity, uint64_t* d_n_out,
-                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters);
+                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters,
+                       uint64_t* d_k_collision);
+/* d_k_collision (device uint64, may be NULL; ADDED to): the generation's collision ("implicit fission") estimator of k,
+ * the one KEigenvalue.hpp:33 lists as to be reimplemented -- every real collision scores nu-bar Sigma_f / Sigma_t of
+ * the material at the pre-collision energy.  Fixed point, MMC_K_COLLISION_ONE per unit score, so that the sum is an
+ * exact integer whatever the scheduling and the number of GPUs: k_collision = sum / MMC_K_COLLISION_ONE / n_in. */
+#define MMC_K_COLLISION_ONE 268435456.0 /* 2^28 */
 
 /* Source bank of the next generation.  The m_total fission sites of all ranks, in global order, are resampled to
  * n_total sources with a deterministic comb: source i <- site floor(i * m_total / n_total); copies of one site get
@@ -369,6 +375,50 @@ int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64
 int mmc_bank_resample(const mmc_world* world, const mmc_site* d_slice, uint64_t slice_first, uint64_t slice_n,
                       uint64_t m_total, uint64_t n_total, uint64_t first_out, uint64_t n_out,
                       const mmc_run_options* options, mmc_site* d_bank_next, uint64_t* d_errors);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch -----------------------------------
+ * The reference's workers are threads of one process (FixedSource.cpp:22-36) and its KEigenvalue::Solve is a stub
+ * (KEigenvalue.cpp:36-62), so nothing here replaces reference code: these are the exchange steps the sharded path
+ * needs.  Fixed source: rank r transports histories [r*N/P, (r+1)*N/P) (mmc_fixed_source_run_device) and the integer
+ * tallies are summed once (mmc_tally_allreduce).  K-eigenvalue: rank r transports source indices [r*N/P, (r+1)*N/P) of
+ * every generation (mmc_generation_run), then mmc_bank_exchange + mmc_bank_resample build its next source bank.
+ * NCCL is loaded at run time (libnccl.so.2); a communicator of one rank needs no NCCL at all. */
+typedef struct mmc_comm mmc_comm;
+#define MMC_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the bytes to every rank (file, MPI, torch.distributed store, ...). */
+int mmc_comm_unique_id(void* id, size_t cap);
+/* ncclCommInitRank on `device` (-1: the current one); collective over the nranks processes. */
+int mmc_comm_create(int nranks, int rank, const void* id, int device, mmc_comm** out);
+void mmc_comm_destroy(mmc_comm* comm);
+int mmc_comm_rank(const mmc_comm* comm);
+int mmc_comm_size(const mmc_comm* comm);
+int mmc_nccl_version(void);            /* ncclGetVersion of the library in use, 0 when NCCL is not available */
+/* Device time (ms, CUDA events on the calls' stream) spent in mmc_bank_exchange so far on this rank. */
+double mmc_comm_exchange_ms(mmc_comm* comm);
+/* In-place sum over the ranks of n_words DEVICE uint64 words (integer tallies, counters, k sums): ncclAllReduce,
+ * asynchronous on `stream` (NULL: the communicator's own stream).  The multi-GPU form of
+ * `solver_estimator_set += worker_estimator_set.get()` (FixedSource.cpp:31-33); exact, so the result is the same for
+ * any number of ranks. */
+int mmc_tally_allreduce(mmc_comm* comm, uint64_t* d_words, size_t n_words, void* stream);
+/* Host-only arithmetic of the exchange (no device, no NCCL): counts[r] = sites banked by rank r this generation, in
+ * global order rank 0's sites first.  need_first / need_count: the global site range the next n_total/P sources of
+ * `rank` are drawn from (source i <- site floor(i * M / n_total)).  send[2*p], send[2*p+1]: start (in this rank's
+ * ordered bank) and count of the sites rank p needs from this rank; recv[2*p], recv[2*p+1]: offset in the rank's
+ * slice and count of the sites it needs from rank p.  Entries with p == rank describe the local copy. */
+int mmc_exchange_plan(const uint64_t* counts, int nranks, int rank, uint64_t n_total, uint64_t* need_first,
+                      uint64_t* need_count, uint64_t* send, uint64_t* recv);
+/* The exchange step of one k-eigenvalue generation.  d_bank_local: this rank's ordered fission bank
+ * (mmc_generation_run's d_bank_out), *d_n_local its size (device).  local_status: non-zero when this rank saw an
+ * error (lost particle, capacity overflow, ...).  All-gathers {size, status} of every rank into counts[nranks] /
+ * statuses[nranks] (HOST, statuses may be NULL) -- one stream synchronisation -- and, unless some status is set or
+ * the bank is empty (then every rank returns MMC_OK with *slice_n = 0 and the caller decides, alike on every rank),
+ * moves the parts of global sites [*slice_first, *slice_first + *slice_n) that live on other ranks into d_slice with
+ * grouped ncclSend / ncclRecv, asynchronously on `stream`.  Follow with mmc_bank_resample(d_slice, *slice_first, ...). */
+int mmc_bank_exchange(mmc_comm* comm, const mmc_site* d_bank_local, const uint64_t* d_n_local, uint64_t local_status,
+                      uint64_t n_total, mmc_site* d_slice, uint64_t slice_capacity, uint64_t* counts, uint64_t* statuses,
+                      uint64_t* slice_first, uint64_t* slice_n, void* stream);
+/* The stream (cudaStream_t) a world's calls run on when mmc_run_options.stream is NULL. */
+void* mmc_world_stream(const mmc_world* world);
 
 /* Device-buffer helpers so that a host without the CUDA toolkit (the C++ host of this repo is compiled by g++) can
  * drive the device-buffer entry points.  All synchronise with the world's stream. */
@@ -455,6 +505,21 @@ int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_hist
 /* k-eigenvalue results of the last Solve(): mean and standard deviation of the
  * mean over active cycles, and k of every cycle (inactive first). */
 int mmc_driver_keff(const mmc_driver* driver, double* k_mean, double* k_std, double* k_cycle, size_t cap, size_t* n_cycles);
+
+/* The collision ("implicit fission", KEigenvalue.hpp:33) estimator of the last Solve(): mean and standard deviation of
+ * the mean over active cycles, the value of every cycle, and the device time (ms) the bank exchanges took. */
+int mmc_driver_k_collision(const mmc_driver* driver, double* k_mean, double* k_std, double* k_cycle, size_t cap,
+                           size_t* n_cycles, double* exchange_ms);
+/* Host time (s) the last k-eigenvalue Solve() spent in its inactive and in its active cycles; every cycle ends with a
+ * device synchronisation, the active time includes the final all-reduce and the read-back of the tallies. */
+int mmc_driver_cycle_seconds(const mmc_driver* driver, double* inactive_seconds, double* active_seconds);
+/* Multi-process runs, one process per GPU: Solve() of a fixed-source deck transports this rank's share of the
+ * histories and all-reduces the integer tallies (every rank then holds the batch's EstimatorSet); Solve() of a
+ * k-eigenvalue deck shards every generation and exchanges the fission bank (mmc_bank_exchange).  The communicator is
+ * not owned by the driver.  _from_environment: MMC_WORLD_SIZE, MMC_RANK, MMC_DEVICE, MMC_COMM_ID_FILE (rank 0
+ * writes the NCCL unique id to that path, the others wait for it) -- a launcher without MPI or torch. */
+int mmc_driver_set_comm(mmc_driver* driver, mmc_comm* comm);
+int mmc_driver_init_comm_from_environment(mmc_driver* driver);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LIB_PATH = Path(__file__).resolve().parent / "libminimc_b200.so"
 
 # enums of include/minimc_b200.h
@@ -110,7 +110,14 @@ EXPORTS = (
     "mmc_driver_add_scores", "mmc_driver_counters", "mmc_driver_output", "mmc_driver_world_json", "mmc_driver_keff",
     "mmc_driver_trace", "mmc_driver_run_device", "mmc_driver_release_device", "mmc_driver_table_bytes", "mmc_world_bytes",
     "mmc_world_update", "mmc_driver_refresh_device", "mmc_world_last_launches", "mmc_driver_last_launches", "mmc_world_last_kernel_ms", "mmc_driver_last_kernel_ms", "mmc_world_last_boundary_ms", "mmc_driver_last_boundary_ms",
+    # multi-GPU
+    "mmc_comm_unique_id", "mmc_comm_create", "mmc_comm_destroy", "mmc_comm_rank", "mmc_comm_size", "mmc_nccl_version",
+    "mmc_comm_exchange_ms", "mmc_tally_allreduce", "mmc_exchange_plan", "mmc_bank_exchange", "mmc_world_stream",
+    "mmc_driver_k_collision", "mmc_driver_cycle_seconds", "mmc_driver_set_comm", "mmc_driver_init_comm_from_environment",
 )
+
+COMM_ID_BYTES = 128
+K_COLLISION_ONE = float(1 << 28)
 
 _lib = None
 
@@ -160,7 +167,7 @@ def load() -> C.CDLL:
     lib.mmc_generation_run.restype = C.c_int
     lib.mmc_generation_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(EstimatorDesc), C.c_int32, C.c_int32,
                                        C.POINTER(RunOptions), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_void_p]
+                                       C.c_void_p, C.c_void_p]
     lib.mmc_bank_resample.restype = C.c_int
     lib.mmc_bank_resample.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                       C.c_uint64, C.POINTER(RunOptions), C.c_void_p, C.c_void_p]
@@ -228,6 +235,38 @@ def load() -> C.CDLL:
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.mmc_driver_keff.restype = C.c_int
     lib.mmc_driver_keff.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.mmc_driver_k_collision.restype = C.c_int
+    lib.mmc_driver_k_collision.argtypes = [C.c_void_p, _pd, _pd, _pd, C.c_size_t, C.POINTER(C.c_size_t), _pd]
+    lib.mmc_driver_cycle_seconds.restype = C.c_int
+    lib.mmc_driver_cycle_seconds.argtypes = [C.c_void_p, _pd, _pd]
+    lib.mmc_driver_set_comm.restype = C.c_int
+    lib.mmc_driver_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mmc_driver_init_comm_from_environment.restype = C.c_int
+    lib.mmc_driver_init_comm_from_environment.argtypes = [C.c_void_p]
+    # multi-GPU
+    lib.mmc_comm_unique_id.restype = C.c_int
+    lib.mmc_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    lib.mmc_comm_create.restype = C.c_int
+    lib.mmc_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mmc_comm_destroy.restype = None
+    lib.mmc_comm_destroy.argtypes = [C.c_void_p]
+    lib.mmc_comm_rank.restype = C.c_int
+    lib.mmc_comm_rank.argtypes = [C.c_void_p]
+    lib.mmc_comm_size.restype = C.c_int
+    lib.mmc_comm_size.argtypes = [C.c_void_p]
+    lib.mmc_nccl_version.restype = C.c_int
+    lib.mmc_comm_exchange_ms.restype = C.c_double
+    lib.mmc_comm_exchange_ms.argtypes = [C.c_void_p]
+    lib.mmc_tally_allreduce.restype = C.c_int
+    lib.mmc_tally_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    _pu64 = C.POINTER(C.c_uint64)
+    lib.mmc_exchange_plan.restype = C.c_int
+    lib.mmc_exchange_plan.argtypes = [_pu64, C.c_int, C.c_int, C.c_uint64, _pu64, _pu64, _pu64, _pu64]
+    lib.mmc_bank_exchange.restype = C.c_int
+    lib.mmc_bank_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
+                                      _pu64, _pu64, _pu64, _pu64, C.c_void_p]
+    lib.mmc_world_stream.restype = C.c_void_p
+    lib.mmc_world_stream.argtypes = [C.c_void_p]
     if lib.mmc_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mmc_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
@@ -422,12 +461,13 @@ class World:
         check(load().mmc_source_bank_sample(self._handle, C.byref(source), seed0, first_index, n, C.byref(o), d_bank))
 
     def generation_run(self, d_bank_in, n_in, estimators, score, d_bank_out, bank_capacity, d_n_out, d_scores, d_square,
-                       d_counters, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0, stream=None):
+                       d_counters, *, tracking=TRACK_SURFACE, secondary_capacity=0, pending_capacity=0, stream=None,
+                       d_k_collision=None):
         """mmc_generation_run: raw device pointers (ints), asynchronous on `stream`."""
         o = self._options(tracking, secondary_capacity, pending_capacity, 0, stream)
         check(load().mmc_generation_run(
             self._handle, d_bank_in, n_in, estimators.array, estimators.n, 1 if score else 0, C.byref(o), d_bank_out,
-            bank_capacity, d_n_out, d_scores, d_square, d_counters))
+            bank_capacity, d_n_out, d_scores, d_square, d_counters, d_k_collision))
 
     def bank_resample(self, d_slice, slice_first, slice_n, m_total, n_total, first_out, n_out, d_bank_next, d_errors, *,
                       stream=None):
@@ -451,6 +491,70 @@ class World:
         check(load().mmc_trace_histories(
             self._handle, C.byref(source), seed0, first_history, n_histories, C.byref(o), records, cap, C.byref(n)))
         return [records[i] for i in range(n.value)]
+
+
+def exchange_plan(counts, n_total: int, rank: int) -> dict:
+    """mmc_exchange_plan (host arithmetic only: no device, no NCCL), in the shape of distributed.exchange_plan."""
+    P = len(counts)
+    c = (C.c_uint64 * P)(*counts)
+    first, count = C.c_uint64(), C.c_uint64()
+    send, recv = (C.c_uint64 * (2 * P))(), (C.c_uint64 * (2 * P))()
+    check(load().mmc_exchange_plan(c, P, rank, n_total, C.byref(first), C.byref(count), send, recv))
+    return {"need": (first.value, count.value),
+            "send": [(p, send[2 * p], send[2 * p + 1]) for p in range(P) if send[2 * p + 1]],
+            "recv": [(p, recv[2 * p], recv[2 * p + 1]) for p in range(P) if recv[2 * p + 1]],
+            "m_total": sum(counts)}
+
+
+class Comm:
+    """mmc_comm: this rank's NCCL communicator (one process per GPU)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        check(load().mmc_comm_unique_id(buf, COMM_ID_BYTES))
+        return buf.raw
+
+    def __init__(self, nranks: int, rank: int, unique_id: bytes | None, device: int = -1):
+        self._handle = C.c_void_p()
+        check(load().mmc_comm_create(nranks, rank, unique_id, device, C.byref(self._handle)))
+
+    @classmethod
+    def from_torch(cls, device: int = -1, group=None):
+        """Rank, size and the unique id's broadcast taken from an initialised torch.distributed group (plumbing only:
+        the communicator and every collective on it are the library's own NCCL calls)."""
+        import torch.distributed as dist
+        rank, size = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 and size > 1 else None]
+        if size > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        return cls(size, rank, box[0], device)
+
+    @property
+    def rank(self) -> int:
+        return load().mmc_comm_rank(self._handle)
+
+    @property
+    def size(self) -> int:
+        return load().mmc_comm_size(self._handle)
+
+    @property
+    def exchange_ms(self) -> float:
+        return float(load().mmc_comm_exchange_ms(self._handle))
+
+    def allreduce(self, d_words: int, n_words: int, stream=None):
+        check(load().mmc_tally_allreduce(self._handle, d_words, n_words, stream))
+
+    def close(self):
+        if self._handle:
+            load().mmc_comm_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Driver:
@@ -499,6 +603,26 @@ class Driver:
 
     def set_shard(self, rank: int, world_size: int):
         check(load().mmc_driver_set_shard(self._handle, rank, world_size))
+
+    def set_comm(self, comm: "Comm"):
+        """Multi-process Solve(): this rank's share of the batch / of every generation, NCCL exchange inside."""
+        self._comm = comm  # keep it alive
+        check(load().mmc_driver_set_comm(self._handle, comm._handle))
+
+    def cycle_seconds(self):
+        """(inactive, active) host seconds of the last k-eigenvalue Solve()."""
+        a, b = C.c_double(), C.c_double()
+        check(load().mmc_driver_cycle_seconds(self._handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def k_collision(self):
+        """(mean, std of the mean, per-cycle values, exchange ms) of the collision estimator of k of the last Solve()."""
+        k_mean, k_std, n, ms = C.c_double(), C.c_double(), C.c_size_t(), C.c_double()
+        check(load().mmc_driver_k_collision(self._handle, C.byref(k_mean), C.byref(k_std), None, 0, C.byref(n), C.byref(ms)))
+        cycles = np.zeros(max(n.value, 1))
+        check(load().mmc_driver_k_collision(self._handle, C.byref(k_mean), C.byref(k_std), _ptr(cycles, C.c_double), n.value,
+                                            C.byref(n), C.byref(ms)))
+        return k_mean.value, k_std.value, cycles[:n.value], ms.value
 
     def solve(self):
         check(load().mmc_driver_solve(self._handle))

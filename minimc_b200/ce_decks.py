@@ -503,6 +503,19 @@ def thermal_fissile_sphere_deck(table_dir, **kw) -> str:
     return free_gas_sphere_deck(table_dir, **kw)
 
 
+def fissile_sphere_keigenvalue_deck(table_dir, *, histories=20000, threads=1, inactive=3, active=8, tracking=None,
+                                    pellet_temperature=290, pellet_radius=12.0) -> str:
+    """A continuous-energy k-eigenvalue problem (SURVEY.md 8f N1; ContinuousFission::Interact in generation mode,
+    ContinuousReaction.cpp:252-265): the fuel / moderator spheres of thermal_fissile_sphere_deck with a larger pellet,
+    isotropic thermal initial source at the centre.  The reference's KEigenvalue::Solve is a stub, so there is no
+    reference result: the analog k (sites banked per source) and the collision estimator of k must agree."""
+    text = free_gas_sphere_deck(table_dir, histories=histories, threads=threads, tracking=tracking, energy=2.53e-8,
+                                pellet_temperature=pellet_temperature)
+    text = text.replace('<radius r="1.5"/>', f'<radius r="{pellet_radius}"/>').replace('<radius r="6"/>', f'<radius r="{pellet_radius + 6}"/>')
+    text = text.replace("  <fixedsource>\n", f'  <keigenvalue inactive="{inactive}" active="{active}">\n  <initialsource>\n')
+    return text.replace("  </fixedsource>\n", "  </initialsource>\n  </keigenvalue>\n")
+
+
 CE_DECKS = {
     "single_zone": slab_deck,
     "multi_zone": multi_zone_deck,

@@ -618,6 +618,8 @@ int mmc_device_count(void) {
 
 uint64_t mmc_world_bytes(const mmc_world* world) { return world ? world->blob_bytes : 0; }
 
+void* mmc_world_stream(const mmc_world* world) { return world ? world->stream : nullptr; }
+
 uint64_t mmc_world_last_launches(const mmc_world* world) { return world ? world->last_launches : 0; }
 
 void mmc_world_last_kernel_ms(const mmc_world* world, double* flight_ms, double* tsl_ms) {
@@ -1091,7 +1093,7 @@ int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source
 int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64_t n_in,
                        const mmc_estimator_desc* estimators, int32_t n_estimators, int32_t score,
                        const mmc_run_options* options, mmc_site* d_bank_out, uint64_t bank_capacity, uint64_t* d_n_out,
-                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters) {
+                       uint64_t* d_scores, uint64_t* d_square_scores, mmc_counters* d_counters, uint64_t* d_k_collision) {
   auto* w = const_cast<mmc_world*>(world);
   if (!w) return fail(MMC_ERR_INVALID, "world handle is NULL");
   std::lock_guard<std::recursive_mutex> run_lock(w->run_mutex);
@@ -1145,6 +1147,7 @@ int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64
   io.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
   io.child_count = w->d_child_count;
   io.child_start = w->d_child_start;
+  io.k_collision = reinterpret_cast<unsigned long long*>(d_k_collision);
   MMC_CUDA(launch_fixed_source(
       p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
       reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
   // was just born from an isotropic source.  Both are the same code on the lane's rng, so they run converged.
   uint32_t owed = 0;
   ThreadCounters c;
+  [[maybe_unused]] unsigned long long k_fixed = 0;  // this thread's collision-estimator scores (generations)
 
   while (true) {
     // ---- refill: next particle of the current history, else a new history
@@ -222,7 +223,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
           p.event = MMC_EV_LEAK;
         }
       }
+      [[maybe_unused]] const uint64_t group_before = p.group;
+      [[maybe_unused]] const double energy_before = p.energy;
       if (p.cell >= 0) transport_step<kTracking, kCE, true, false, kPerturb>(w, p, dq, o, &pc);
+      if (kGeneration && bank.k_collision &&
+          (p.event == MMC_EV_SCATTER || p.event == MMC_EV_CAPTURE || p.event == MMC_EV_FISSION) && !o.error_physics) {
+        // collision estimator of k at the collision site, pre-collision energy (see implicit_fission_score)
+        const int32_t mat = w.at<int32_t>(w.h->off_cell_material)[p.cell];
+        const double T = kCE ? ce::cell_temperature(w, p.cell, p.px, p.py, p.pz) : 0.0;
+        k_fixed += static_cast<unsigned long long>(
+            __double2ll_rn(__dmul_rn(implicit_fission_score<kCE>(w, mat, group_before, energy_before, T), 268435456.0)));
+      }
       if (o.need_direction) owed |= 1u;
       count_event(c, p, o);
     }
@@ -307,6 +318,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
     }
   }
   commit_sensitivities();
+  if (kGeneration && bank.k_collision) {
+    for (int d = 16; d > 0; d >>= 1) k_fixed += __shfl_down_sync(kFull, k_fixed, d);
+    if (lane == 0 && k_fixed) atomicAdd(bank.k_collision, k_fixed);
+  }
 
   flush_counter(&counters->n_histories, c.histories);
   flush_counter(&counters->n_births, c.births);

@@ -23,6 +23,7 @@ struct GenerationIO {
   unsigned long long* n_out = nullptr;       // sites claimed so far
   uint32_t* child_count = nullptr;           // [n_histories] secondaries of each source particle
   unsigned long long* child_start = nullptr; // [n_histories] where that particle's run starts in `out`
+  unsigned long long* k_collision = nullptr; // sum of the collision estimator's scores, fixed point (MMC_K_COLLISION_ONE); may be null
 };
 
 // fills the dense reconstruction tables of the device-only tail of the image (world_blob.h DenseJob)

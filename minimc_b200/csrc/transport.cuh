@@ -588,6 +588,42 @@ __device__ __forceinline__ void transport_step(
   }
 }
 
+// Collision ("implicit fission") estimator of k, the one KEigenvalue.hpp:33 lists as to be reimplemented: every real
+// collision scores nu-bar Sigma_f / Sigma_t of the material at the particle's pre-collision energy, whatever the
+// reaction sampled next.  Sums in nuclide order from 0.0; the caller adds the score as a fixed-point integer
+// (MMC_K_COLLISION_ONE = 2^28) so that the generation's sum is independent of scheduling and GPU count.
+template <bool kCE>
+__device__ inline double implicit_fission_score(const WorldView& w, int32_t mat, uint64_t group, double E, double T) {
+  const int32_t* nb = w.at<int32_t>(w.h->off_mat_nuc_begin);
+  const int32_t* ni = w.at<int32_t>(w.h->off_mat_nuc_index);
+  const double* af = w.at<double>(w.h->off_mat_nuc_afrac);
+  double nu_fission = 0, total = 0;
+  if (kCE) {
+    const CeNuclide* nuclides = w.at<CeNuclide>(w.h->off_ce_nuclides);
+    bool error = false;
+    for (int32_t k = nb[mat]; k < nb[mat + 1]; k++) {
+      const CeNuclide& n = nuclides[ni[k]];
+      total = __dadd_rn(total, __dmul_rn(af[k], ce::nuclide_total(w, n, E, T, error)));
+      for (int32_t r = 0; r < n.n_reactions; r++)
+        if (n.reactions[r].kind == MMC_REACTION_FISSION && n.reactions[r].nubar.n)
+          nu_fission = __dadd_rn(nu_fission, __dmul_rn(af[k], __dmul_rn(ce::table_at(w, n.reactions[r].nubar, E),
+                                                                      ce::table_at(w, n.reactions[r].xs, E))));
+    }
+  } else {
+    const int32_t G = w.h->n_groups;
+    const double* tot = w.at<double>(w.h->off_mg_total);
+    const double* fis = w.at<double>(w.h->off_mg_fission);
+    const double* nubar = w.at<double>(w.h->off_mg_nubar);
+    const uint32_t* mask = w.at<uint32_t>(w.h->off_mg_mask);
+    for (int32_t k = nb[mat]; k < nb[mat + 1]; k++) {
+      const int32_t i = ni[k] * G + static_cast<int32_t>(group - 1);
+      total = __dadd_rn(total, __dmul_rn(af[k], tot[i]));
+      if (mask[ni[k]] & MMC_REACTION_FISSION) nu_fission = __dadd_rn(nu_fission, __dmul_rn(af[k], __dmul_rn(nubar[i], fis[i])));
+    }
+  }
+  return total > 0 ? __ddiv_rn(nu_fission, total) : 0.0;
+}
+
 // ------------------------------------------------------------------- tallies
 // Bins::GetIndex for each concrete type, Bins.cpp:72-82,112-123,158-162
 static __device__ __noinline__ uint64_t bins_index(const BinsSpec& b, const double* bounds, double v) {

@@ -1,8 +1,13 @@
 // Driver / FixedSource / KEigenvalue: the reference's batch-level seam
 // (Driver.hpp:23-30).  Solve() hands the whole batch to the GPU through the C
 // ABI; there is no host transport loop.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
+#include <thread>
 
 #include "minimc.hpp"
 
@@ -98,7 +103,52 @@ Driver::Driver(const xml::Node& root)
   run_options.rng_mode = MMC_RNG_MINSTD_COMPAT;
 }
 
-Driver::~Driver() noexcept {}
+Driver::~Driver() noexcept {
+  if (owned_comm_) mmc_comm_destroy(owned_comm_);
+}
+
+void Driver::SetComm(mmc_comm* c) {
+  comm = c;
+  rank = mmc_comm_rank(c);
+  world_size = mmc_comm_size(c);
+}
+
+void Driver::InitCommFromEnvironment() {
+  const char* ws = std::getenv("MMC_WORLD_SIZE");
+  const int P = ws ? std::atoi(ws) : 1;
+  if (P <= 1) return;
+  const char* rk = std::getenv("MMC_RANK");
+  const char* file = std::getenv("MMC_COMM_ID_FILE");
+  if (!rk || !file) throw std::runtime_error("MMC_WORLD_SIZE > 1 needs MMC_RANK and MMC_COMM_ID_FILE");
+  const int R = std::atoi(rk);
+  const char* dev = std::getenv("MMC_DEVICE");
+  const int device = dev ? std::atoi(dev) : R;
+  run_options.device = device;
+  unsigned char id[MMC_COMM_ID_BYTES];
+  const std::string path = file, tmp = path + ".tmp";
+  if (R == 0) {
+    if (const int status = mmc_comm_unique_id(id, sizeof(id))) ThrowLastError("mmc_comm_unique_id", status);
+    std::FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw std::runtime_error("cannot write " + tmp);
+    std::fclose(f);
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot rename " + tmp);
+  } else {
+    // the file appears atomically (rename) once rank 0 has written all of it
+    for (int waited_ms = 0;; waited_ms += 20) {
+      if (std::FILE* f = std::fopen(path.c_str(), "rb")) {
+        const size_t n = std::fread(id, 1, sizeof(id), f);
+        std::fclose(f);
+        if (n == sizeof(id)) break;
+      }
+      if (waited_ms > 120000) throw std::runtime_error("timed out waiting for " + path);
+      std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+  }
+  mmc_comm* c = nullptr;
+  if (const int status = mmc_comm_create(P, R, id, device, &c)) ThrowLastError("mmc_comm_create", status);
+  owned_comm_ = c;
+  SetComm(c);
+}
 
 std::shared_ptr<DeviceWorld> Driver::device_world() {
   if (!device_world_) device_world_ = std::make_shared<DeviceWorld>(world, run_options.device);
@@ -137,6 +187,43 @@ EstimatorSet FixedSource::Solve() {
       sensitivity_bins += s.scores.size();
     }
   std::vector<double> sens_scores(sensitivity_bins, 0.0), sens_square_scores(sensitivity_bins, 0.0);
+  if (comm && world_size > 1) {
+    // One process per GPU: this rank's histories with DEVICE tallies, then ONE all-reduce of the packed integer words
+    // [scores | squares | counters] -- the multi-GPU form of `solver_estimator_set += worker_estimator_set.get()`
+    // (FixedSource.cpp:31-33).  Every rank returns the whole batch's EstimatorSet.
+    if (!sensitivities.empty())
+      throw std::runtime_error("sensitivities are real-valued tallies: reduce the ranks' EstimatorSets with operator+= instead");
+    const mmc_world* w = device_world()->handle;
+    const size_t bins = result.total_bins();
+    constexpr size_t kCounterWords = sizeof(mmc_counters) / sizeof(uint64_t);
+    const size_t words = 2 * bins + kCounterWords;
+    void* d_ptr = nullptr;
+    if (const int st = mmc_device_alloc(w, words * sizeof(uint64_t), &d_ptr)) ThrowLastError("mmc_device_alloc", st);
+    uint64_t* d_words = static_cast<uint64_t*>(d_ptr);
+    mmc_run_options options = run_options;
+    options.stream = run_options.stream ? run_options.stream : mmc_world_stream(w);
+    int st = mmc_fixed_source_run_device(w, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()), seed, first,
+                                         last - first, &options, d_words, d_words + bins,
+                                         reinterpret_cast<mmc_counters*>(d_words + 2 * bins));
+    if (st == MMC_OK) st = mmc_tally_allreduce(comm, d_words, words, options.stream);
+    std::vector<uint64_t> h_words(words);
+    if (st == MMC_OK) st = mmc_device_read(w, h_words.data(), d_words, words * sizeof(uint64_t));
+    mmc_device_free(w, d_ptr);
+    if (st != MMC_OK) ThrowLastError("FixedSource::Solve (multi-rank)", st);
+    std::memcpy(&counters, h_words.data() + 2 * bins, sizeof(counters));
+    if (counters.n_lost) throw DeviceError(MMC_ERR_LOST_PARTICLE, "FixedSource::Solve: particle(s) outside every cell");
+    if (counters.n_physics_errors) throw DeviceError(MMC_ERR_PHYSICS, "FixedSource::Solve: a branch the reference asserts unreachable was reached");
+    if (counters.n_capacity_overflow) throw DeviceError(MMC_ERR_CAPACITY, "FixedSource::Solve: per-history capacity overflow");
+    size_t at = 0;
+    for (Estimator& e : result.estimators) {
+      for (size_t i = 0; i < e.scores.size(); i++) {
+        e.scores[i] += static_cast<Real>(h_words[at + i]);
+        e.square_scores[i] += static_cast<Real>(h_words[bins + at + i]);
+      }
+      at += e.scores.size();
+    }
+    return result;
+  }
   const int status = mmc_fixed_source_run_sensitivities(
       device_world()->handle, &source.desc, estimators.data(), static_cast<int32_t>(estimators.size()),
       sensitivities.data(), static_cast<int32_t>(sensitivities.size()), seed, first, last - first, &run_options,

@@ -223,6 +223,43 @@ int mmc_driver_trace(mmc_driver* driver, uint64_t first_history, uint64_t n_hist
   });
 }
 
+int mmc_driver_set_comm(mmc_driver* driver, mmc_comm* comm) {
+  if (!driver || !comm) return mmc::set_last_error(MMC_ERR_INVALID, "driver / comm is NULL");
+  driver->driver->SetComm(comm);
+  return MMC_OK;
+}
+
+int mmc_driver_init_comm_from_environment(mmc_driver* driver) {
+  return Guard([&] {
+    if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
+    driver->driver->InitCommFromEnvironment();
+    return static_cast<int>(MMC_OK);
+  });
+}
+
+int mmc_driver_k_collision(const mmc_driver* driver, double* k_mean, double* k_std, double* k_cycle, size_t cap, size_t* n_cycles,
+                           double* exchange_ms) {
+  if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
+  const auto* k = dynamic_cast<const minimc::KEigenvalue*>(driver->driver.get());
+  if (!k) return mmc::set_last_error(MMC_ERR_INVALID, "not a k-eigenvalue problem");
+  if (k_mean) *k_mean = k->result().k_collision_mean;
+  if (k_std) *k_std = k->result().k_collision_std;
+  if (n_cycles) *n_cycles = k->result().k_collision_cycle.size();
+  if (k_cycle)
+    for (size_t i = 0; i < std::min(cap, k->result().k_collision_cycle.size()); i++) k_cycle[i] = k->result().k_collision_cycle[i];
+  if (exchange_ms) *exchange_ms = k->result().exchange_ms;
+  return MMC_OK;
+}
+
+int mmc_driver_cycle_seconds(const mmc_driver* driver, double* inactive_seconds, double* active_seconds) {
+  if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
+  const auto* k = dynamic_cast<const minimc::KEigenvalue*>(driver->driver.get());
+  if (!k) return mmc::set_last_error(MMC_ERR_INVALID, "not a k-eigenvalue problem");
+  if (inactive_seconds) *inactive_seconds = k->result().inactive_seconds;
+  if (active_seconds) *active_seconds = k->result().active_seconds;
+  return MMC_OK;
+}
+
 int mmc_driver_keff(const mmc_driver* driver, double* k_mean, double* k_std, double* k_cycle, size_t cap, size_t* n_cycles) {
   if (!driver) return mmc::set_last_error(MMC_ERR_INVALID, "driver is NULL");
   const auto* k = dynamic_cast<const minimc::KEigenvalue*>(driver->driver.get());

@@ -276,6 +276,13 @@ struct KResult {
   std::vector<Real> k_cycle;  // one per cycle (inactive then active)
   Real k_mean = 0, k_std = 0; // over active cycles
   std::vector<uint64_t> bank_sizes;
+  // collision ("implicit fission", KEigenvalue.hpp:33) estimator: sum over real collisions of nu Sigma_f / Sigma_t, per source
+  std::vector<Real> k_collision_cycle;
+  Real k_collision_mean = 0, k_collision_std = 0;
+  double exchange_ms = 0;     // device time of the bank exchanges (multi-rank runs)
+  // host time of the inactive and of the active cycles (each cycle ends with a device synchronisation; the active
+  // time includes the final all-reduce and the read-back of the tallies)
+  double inactive_seconds = 0, active_seconds = 0;
 };
 
 // Driver (Driver.cpp:19-52)
@@ -301,6 +308,13 @@ public:
   // rank / world_size sharding of histories [0, batchsize): rank r owns
   // [r*N/P, (r+1)*N/P); the caller reduces EstimatorSets with operator+=
   int rank = 0, world_size = 1;
+  // multi-process runs (one process per GPU): the NCCL communicator of this rank, not owned unless created by
+  // InitCommFromEnvironment.  SetComm also sets rank / world_size.
+  mmc_comm* comm = nullptr;
+  void SetComm(mmc_comm* c);
+  // MMC_WORLD_SIZE > 1 in the environment: MMC_RANK, MMC_DEVICE (default: rank) and MMC_COMM_ID_FILE, a path every rank
+  // can reach -- rank 0 writes the NCCL unique id there, the others wait for it.  A launcher without MPI or torch.
+  void InitCommFromEnvironment();
   mmc_counters counters{};
   // Drops the device copy of the World (the next Solve() uploads it again); bytes it holds.
   void ReleaseDevice() { device_world_.reset(); }
@@ -315,6 +329,7 @@ protected:
 
 private:
   std::shared_ptr<DeviceWorld> device_world_;
+  mmc_comm* owned_comm_ = nullptr;
 };
 
 // FixedSource (FixedSource.cpp:19-77)

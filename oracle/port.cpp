@@ -188,6 +188,16 @@ struct World {
       acc = acc + w.material_nuclide_afrac[k] * NuclideTotal(w.material_nuclide_index[k], g);
     return acc;
   }
+  double ImplicitFission(int32_t mat, uint64_t g) const {
+    double nu_fission = 0, total = 0;
+    for (int32_t k = w.material_nuclide_begin[mat]; k < w.material_nuclide_begin[mat + 1]; k++) {
+      const int32_t nuc = w.material_nuclide_index[k];
+      const int32_t i = nuc * w.n_groups + static_cast<int32_t>(g - 1);
+      total = total + w.material_nuclide_afrac[k] * w.mg_total[i];
+      if (w.mg_reaction_mask[nuc] & 4u) nu_fission = nu_fission + w.material_nuclide_afrac[k] * (w.mg_nubar[i] * w.mg_fission[i]);
+    }
+    return total > 0 ? nu_fission / total : 0.0;
+  }
 };
 
 struct Errors {
@@ -276,7 +286,8 @@ void Stream(Particle& p, double distance) {  // Particle.cpp:46-53
 // CellDeltaTracking::Transport (TransportMethod.cpp:88-122).  `score` is
 // EstimatorSetProxy::Score.
 template <typename ScoreFn>
-void Transport(const World& W, Particle& p, int tracking, Errors& err, orc_counters& cnt, ScoreFn&& score) {
+void Transport(const World& W, Particle& p, int tracking, Errors& err, orc_counters& cnt, ScoreFn&& score,
+               uint64_t* k_collision_fixed = nullptr) {
   const orc_world& w = W.w;
   p.cell = W.FindCellContaining(p.position);
   if (p.cell < 0) {
@@ -318,6 +329,9 @@ void Transport(const World& W, Particle& p, int tracking, Errors& err, orc_count
       }
       Stream(p, distance_to_collision);
       if (real) {
+        // collision ("implicit fission", KEigenvalue.hpp:33) estimator of k: nu Sigma_f / Sigma_t of the material at the
+        // pre-collision group, as a fixed-point integer (2^28 per unit) -- DESIGN.md "k-eigenvalue"
+        if (k_collision_fixed) *k_collision_fixed += static_cast<uint64_t>(std::llrint(W.ImplicitFission(mat, p.group) * 268435456.0));
         const int32_t nuc = SampleNuclide(W, p, mat);
         if (nuc < 0) {
           err.physics++;
@@ -531,7 +545,7 @@ size_t orc_trace(
 int orc_keigenvalue_run(
     const orc_world* world, const orc_source* source, const orc_estimator* estimators, int32_t n_estimators,
     uint64_t batchsize, uint64_t inactive, uint64_t active, int32_t tracking, double* scores, double* square_scores,
-    double* k_cycle, uint64_t* bank_sizes, orc_counters* counters) {
+    double* k_cycle, uint64_t* bank_sizes, orc_counters* counters, double* k_collision_cycle) {
   const World W{*world};
   const Tally tally{estimators, n_estimators};
   orc_counters cnt{};
@@ -549,6 +563,7 @@ int orc_keigenvalue_run(
   }
   for (uint64_t cycle = 0; cycle < inactive + active; cycle++) {
     const bool score = cycle >= inactive;
+    uint64_t k_fixed = 0;
     std::vector<Site> fission_bank;
     for (const Site& site : bank) {
       Particle p;
@@ -563,7 +578,7 @@ int orc_keigenvalue_run(
       Transport(W, p, tracking, err, cnt, [&](const Particle& q) {
         if (score) tally.Score(q, pending, cnt);
         else tally.Score(q, pending, scratch);
-      });
+      }, &k_fixed);
       if (score)
         for (const auto& [index, s] : pending) {
           scores[index] += s;
@@ -575,6 +590,7 @@ int orc_keigenvalue_run(
     const uint64_t M = fission_bank.size(), N = batchsize;
     k_cycle[cycle] = static_cast<double>(M) / static_cast<double>(N);
     bank_sizes[cycle] = M;
+    if (k_collision_cycle) k_collision_cycle[cycle] = static_cast<double>(k_fixed) / 268435456.0 / static_cast<double>(N);
     if (M == 0) break;
     // comb resampling: source i <- site floor(i * M / N); copies get seed + copy ordinal
     std::vector<Site> next;

@@ -95,11 +95,12 @@ size_t orc_trace(
     orc_record* records, size_t cap);
 
 /* K-eigenvalue power iteration as defined in DESIGN.md "k-eigenvalue" (the reference has none: parity with the
- * reference is unpinned here).  k_cycle / bank_sizes have inactive + active entries; tallies cover active cycles. */
+ * reference is unpinned here).  k_cycle / bank_sizes / k_collision_cycle (the collision estimator of k: nu Sigma_f / Sigma_t at every real collision,
+ * summed in 2^-28 fixed point, per source) have inactive + active entries; tallies cover active cycles. */
 int orc_keigenvalue_run(
     const orc_world* world, const orc_source* source, const orc_estimator* estimators, int32_t n_estimators,
     uint64_t batchsize, uint64_t inactive, uint64_t active, int32_t tracking, double* scores, double* square_scores,
-    double* k_cycle, uint64_t* bank_sizes, orc_counters* counters);
+    double* k_cycle, uint64_t* bank_sizes, orc_counters* counters, double* k_collision_cycle /* may be NULL */);
 
 /* n canonical doubles + engine states from std::minstd_rand{seed}, restated. */
 void orc_rng_canonical(uint64_t seed, size_t n, double* u, uint64_t* state);

@@ -85,7 +85,7 @@ def load():
         lib.orc_keigenvalue_run.restype = C.c_int
         lib.orc_keigenvalue_run.argtypes = [
             C.POINTER(OrcWorld), C.POINTER(OrcSource), C.POINTER(OrcEstimator), C.c_int32, C.c_uint64, C.c_uint64,
-            C.c_uint64, C.c_int32, _pd, _pd, _pd, C.POINTER(C.c_uint64), C.POINTER(OrcCounters)]
+            C.c_uint64, C.c_int32, _pd, _pd, _pd, C.POINTER(C.c_uint64), C.POINTER(OrcCounters), _pd]
         lib.orc_rng_canonical.restype = None
         lib.orc_rng_canonical.argtypes = [C.c_uint64, C.c_size_t, _pd, C.POINTER(C.c_uint64)]
         _lib = lib
@@ -169,10 +169,11 @@ class Problem:
         k = np.zeros(inactive + active)
         sizes = np.zeros(inactive + active, np.uint64)
         counters = OrcCounters()
+        self.k_collision = np.zeros(inactive + active)  # the collision estimator of k, per cycle
         status = load().orc_keigenvalue_run(
             C.byref(self.world), C.byref(self.source), self.estimators, self.n_estimators, n, inactive, active,
             tracking, scores.ctypes.data_as(_pd), squares.ctypes.data_as(_pd), k.ctypes.data_as(_pd),
-            sizes.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(counters))
+            sizes.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(counters), self.k_collision.ctypes.data_as(_pd))
         return scores[:self.total_bins], squares[:self.total_bins], k, sizes, counters.as_dict(), status
 
     def trace(self, first, n, *, seed0=None, tracking=None, cap=1 << 16):

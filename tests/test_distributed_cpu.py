@@ -124,3 +124,22 @@ def test_gloo_bank_exchange_delivers_the_global_order(tmp_path, counts, n_total)
         i_lo, n = distributed.shard(0, n_total, rank, P)
         js = np.array([i * M // n_total for i in range(i_lo, i_lo + n)])
         assert first == js[0] and np.array_equal(got, np.arange(js[0], js[-1] + 1))
+
+
+def test_c_abi_exchange_plan_equals_the_python_plan():
+    """mmc_exchange_plan (the host arithmetic of mmc_bank_exchange; no device, no NCCL) against
+    distributed.exchange_plan on random bank sizes, including empty ranks, one rank and more ranks than sources."""
+    import random
+    from minimc_b200 import capi
+    rng = random.Random(20261018)
+    for P in (1, 2, 3, 8):
+        for _ in range(40):
+            n_total = rng.choice([1, 5, 1000, 12345, 10**9 + 7])
+            counts = [rng.choice([0, rng.randrange(0, 3 * max(n_total // P, 1) + 1)]) for _ in range(P)]
+            if sum(counts) == 0:
+                counts[rng.randrange(P)] = 1
+            for rank in range(P):
+                a = capi.exchange_plan(counts, n_total, rank)
+                b = distributed.exchange_plan(counts, n_total, rank)
+                assert a["need"] == tuple(b["need"]) and a["m_total"] == b["m_total"]
+                assert a["send"] == [tuple(x) for x in b["send"]] and a["recv"] == [tuple(x) for x in b["recv"]]

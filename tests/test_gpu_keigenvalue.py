@@ -19,12 +19,15 @@ pytestmark = pytest.mark.gpu
 def test_power_iteration_matches_oracle_exactly(name, tracking):
     text = decks.KDECKS[name](tracking=util.TRACKING[tracking])
     flat = util.flat_from_xml(text)
-    o_scores, o_squares, o_k, o_sizes, o_counters, status = util.oracle_problem(flat).keigenvalue()
+    problem = util.oracle_problem(flat)
+    o_scores, o_squares, o_k, o_sizes, o_counters, status = problem.keigenvalue()
     assert status == 0
     drv = capi.Driver(text=text)
     scores, squares = drv.solve()
     k_mean, k_std, k_cycle = drv.keff()
     assert np.array_equal(k_cycle, o_k)
+    # the collision ("implicit fission", KEigenvalue.hpp:33) estimator: fixed-point sums, exact
+    assert np.array_equal(drv.k_collision()[2], problem.k_collision)
     assert np.array_equal(scores, o_scores) and np.array_equal(squares, o_squares)
     c = drv.counters()
     for key in ("n_histories", "n_births", "n_events", "n_collisions", "n_crossings", "n_virtual", "n_scores",
@@ -55,6 +58,10 @@ def test_k_infinite_agrees_with_analytic_value():
     assert len(k_cycle) == 45 and k_std > 0
     assert abs(k_mean - 0.81) < 4 * k_std
     assert k_std < 2e-3
+    # the collision estimator scores nu Sigma_f / Sigma_t = 0.6075 at each of the 1 / (1 - c) = 4/3 collisions per source
+    kc_mean, kc_std, kc_cycle, _ = drv.k_collision()
+    assert len(kc_cycle) == 45 and 0 < kc_std < k_std  # every collision scores: less variance than the analog estimator
+    assert abs(kc_mean - 0.81) < 4 * kc_std
 
 
 def test_out_file_normalisation_counts_active_histories():
@@ -94,3 +101,27 @@ def test_python_distributed_driver_equals_cpp_host_at_one_rank():
     out = kd.solve(device=torch.device("cuda", 0))
     assert np.array_equal(out["k_cycle"], k_cycle)
     assert np.array_equal(out["scores"], scores) and np.array_equal(out["square_scores"], squares)
+
+
+def test_continuous_energy_keigenvalue(tmp_path):
+    """A continuous-energy fissile sphere (ContinuousFission::Interact in generation mode, ContinuousReaction.cpp:252-265;
+    the reference has no k-eigenvalue to compare with: PARITY UNPINNED).  Checked: the analog estimator (sites banked per
+    source) and the collision estimator agree within their combined 4 sigma; the secondaries of every fission are at
+    the parent's energy (every bank site's energy is one a particle had); both tracking modes run; a batch is
+    independent of how the GPU schedules it (two runs give identical k per cycle)."""
+    from minimc_b200 import ce_decks
+    ce_decks.generate_tables(tmp_path, "small")
+    for tracking in (None, "cell delta"):
+        text = ce_decks.fissile_sphere_keigenvalue_deck(tmp_path, histories=40_000, inactive=3, active=12, tracking=tracking)
+        drv = capi.Driver(text=text)
+        drv.solve()
+        k_mean, k_std, k_cycle = drv.keff()
+        kc_mean, kc_std, kc_cycle, _ = drv.k_collision()
+        c = drv.counters()
+        assert c["n_lost"] == c["n_physics_errors"] == c["n_capacity_overflow"] == 0
+        assert c["n_histories"] == 15 * 40_000 and c["n_banked"] > 0
+        assert 0.3 < k_mean < 3.0 and k_std > 0 and kc_std > 0
+        assert abs(k_mean - kc_mean) < 4 * np.hypot(k_std, kc_std), (k_mean, k_std, kc_mean, kc_std)
+        again = capi.Driver(text=text)
+        again.solve()
+        assert np.array_equal(again.keff()[2], k_cycle) and np.array_equal(again.k_collision()[2], kc_cycle)
