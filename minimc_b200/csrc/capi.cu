@@ -1154,7 +1154,7 @@ int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64
       &io, p.stream));
   MMC_CUDA(launch_order_bank(
       w->d_child_count, w->d_child_start, n_in, w->d_block_sums, w->d_unordered, reinterpret_cast<BankSite*>(d_bank_out),
-      p.stream));
+      reinterpret_cast<unsigned long long*>(d_n_out), p.stream));
   return MMC_OK;
 }
 

@@ -140,6 +140,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
   uint32_t owed = 0;
   ThreadCounters c;
   [[maybe_unused]] unsigned long long k_fixed = 0;  // this thread's collision-estimator scores (generations)
+  // generations: the fission secondaries this lane's dead particle still owes the bank.  The reference makes them in
+  // a loop inside Fission (Multigroup.cpp:267-287, ContinuousReaction.cpp:252-265); with one lane in four fissioning
+  // per collision that loop would run in every warp at a quarter of its lanes.  Here the fission only draws its yield
+  // and claims its run of the bank; the sites are made one per loop iteration from the parent's rng, in the same
+  // draw order, converged with the isotropic directions the other lanes owe (scatter, birth).
+  [[maybe_unused]] uint32_t sites_owed = 0, sites_made = 0;
+  [[maybe_unused]] unsigned long long site_start = 0;
+  [[maybe_unused]] int32_t fission_nuclide = -1;
 
   while (true) {
     // ---- refill: next particle of the current history, else a new history
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
       alive = true;
       c.births++;
     }
-    const bool need = !alive && !done;
+    const bool need = !alive && !done && !(kGeneration && sites_owed);
     const unsigned need_mask = __ballot_sync(kFull, need);
     if (need_mask) {
       const uint32_t n = __popc(need_mask);
@@ -202,7 +210,55 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
     if (__all_sync(kFull, done)) break;
 
     // ---- isotropic directions owed to scattered and newly born lanes (Point.cpp:89-96)
-    if (owed) {
+    if (kGeneration) {
+      if (owed || sites_owed) {
+        const bool make = sites_owed != 0;
+        // Multigroup::Fission: the secondary's group from chi (no group found: no secondary, Multigroup.cpp:278-283)
+        uint64_t child_group = 0;
+        bool site_ok = true;
+        if (make && !kCE) {
+          const int32_t G = w.h->n_groups;
+          const double* chi = w.at<double>(w.h->off_mg_chi) + (static_cast<size_t>(fission_nuclide) * G + (p.group - 1)) * G;
+          const double t = p.rng.canonical();
+          double a = 0.0;
+          site_ok = false;
+          for (int32_t g = 0; g < G; g++) {
+            a = __dadd_rn(a, chi[g]);
+            if (a > t) {
+              child_group = static_cast<uint64_t>(g + 1);
+              site_ok = true;
+              break;
+            }
+          }
+        }
+        if (site_ok) {
+          double ix, iy, iz;
+          isotropic_direction(p.rng, ix, iy, iz);
+          if (make) {
+            BankSite s;
+            s.position[0] = p.px, s.position[1] = p.py, s.position[2] = p.pz;
+            s.direction[0] = ix, s.direction[1] = iy, s.direction[2] = iz;
+            s.energy_bits = kCE ? static_cast<uint64_t>(__double_as_longlong(p.energy)) : child_group;
+            s.seed = p.rng.raw();  // Particle::BankSecondaries, Particle.cpp:96-100
+            s.surface = -1;
+            bank.out[site_start + sites_made] = s;
+            sites_made++;
+          } else {
+            p.dx = ix, p.dy = iy, p.dz = iz;
+            if (owed & 2u) finish_source(p);
+          }
+        }
+        if (make) {
+          if (--sites_owed == 0) {
+            bank.child_count[history] = sites_made;
+            c.secondaries += sites_made;
+            c.banked += sites_made;
+          }
+        } else {
+          owed = 0;
+        }
+      }
+    } else if (owed) {
       isotropic_direction(p.rng, p.dx, p.dy, p.dz);
       if (owed & 2u) finish_source(p);
       owed = 0;
@@ -225,7 +281,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
       }
       [[maybe_unused]] const uint64_t group_before = p.group;
       [[maybe_unused]] const double energy_before = p.energy;
-      if (p.cell >= 0) transport_step<kTracking, kCE, true, false, kPerturb>(w, p, dq, o, &pc);
+      if (p.cell >= 0) transport_step<kTracking, kCE, true, false, kPerturb, false, kGeneration>(w, p, dq, o, &pc);
       if (kGeneration && bank.k_collision &&
           (p.event == MMC_EV_SCATTER || p.event == MMC_EV_CAPTURE || p.event == MMC_EV_FISSION) && !o.error_physics) {
         // collision estimator of k at the collision site, pre-collision energy (see implicit_fission_score)
@@ -238,8 +294,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
       count_event(c, p, o);
     }
     if (kGeneration) {
-      // ---- bank this event's fission secondaries (the parent is dead: it fissioned)
-      const uint32_t mine = alive ? dq.count : 0u;
+      // ---- a fission claims its run of the fission bank: one aggregated atomic per warp, each parent's run contiguous
+      const uint32_t mine = alive ? o.pending_yield : 0u;
       const unsigned any = __ballot_sync(kFull, mine != 0);
       if (any) {
         uint32_t inclusive = mine;
@@ -254,14 +310,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
         if (mine) {
           const unsigned long long start = base + (inclusive - mine);
           if (start + mine <= bank.capacity) {
-            for (uint32_t k = 0; k < mine; k++) bank.out[start + k] = dq.slots[(dq.head + k) & dq.mask];
-            bank.child_count[history] = mine;
+            site_start = start;
+            sites_owed = mine;
+            sites_made = 0;
+            fission_nuclide = o.fission_nuclide;
             bank.child_start[history] = start;
-            c.banked += mine;
           } else {
             c.capacity++;
           }
-          dq.count = 0;
         }
       }
     }
@@ -491,7 +547,8 @@ __global__ void __launch_bounds__(kScanThreads) bank_block_sums_kernel(
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) bank_scan_block_sums_kernel(unsigned long long* block_sums, uint32_t n_blocks) {
+__global__ void __launch_bounds__(kScanThreads) bank_scan_block_sums_kernel(unsigned long long* block_sums, uint32_t n_blocks,
+                                                                           unsigned long long* n_sites) {
   // one block walks the block sums in tiles (n_blocks <= n_parents / 1024)
   __shared__ uint32_t smem_warp[33];
   __shared__ unsigned long long carry;
@@ -507,6 +564,9 @@ __global__ void __launch_bounds__(kScanThreads) bank_scan_block_sums_kernel(unsi
     if (threadIdx.x == 0) carry += total;
     __syncthreads();
   }
+  // the bank's size: the sites MADE (a claimed run can end in unused slots: a secondary whose group walk over chi
+  // found no group is not made, Multigroup.cpp:278-283), not the slots claimed
+  if (threadIdx.x == 0 && n_sites) *n_sites = carry;
 }
 
 __global__ void __launch_bounds__(kScanThreads) order_bank_kernel(
@@ -623,11 +683,11 @@ uint32_t bank_scan_blocks(uint64_t n_parents) { return static_cast<uint32_t>((n_
 
 cudaError_t launch_order_bank(
     const uint32_t* child_count, const unsigned long long* child_start, uint64_t n_parents, unsigned long long* block_sums,
-    const BankSite* unordered, BankSite* ordered, cudaStream_t stream) {
+    const BankSite* unordered, BankSite* ordered, unsigned long long* n_sites, cudaStream_t stream) {
   if (n_parents == 0) return cudaSuccess;
   const uint32_t blocks = bank_scan_blocks(n_parents);
   bank_block_sums_kernel<<<blocks, kScanThreads, 0, stream>>>(child_count, n_parents, block_sums);
-  bank_scan_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, blocks);
+  bank_scan_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(block_sums, blocks, n_sites);
   order_bank_kernel<<<blocks, kScanThreads, 0, stream>>>(child_count, child_start, n_parents, block_sums, unordered, ordered);
   return cudaGetLastError();
 }

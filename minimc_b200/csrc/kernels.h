@@ -35,7 +35,7 @@ cudaError_t launch_source_bank(const RunSpec& run, BankSite* bank, cudaStream_t 
 uint32_t bank_scan_blocks(uint64_t n_parents);
 cudaError_t launch_order_bank(
     const uint32_t* child_count, const unsigned long long* child_start, uint64_t n_parents, unsigned long long* block_sums,
-    const BankSite* unordered, BankSite* ordered, cudaStream_t stream);
+    const BankSite* unordered, BankSite* ordered, unsigned long long* n_sites, cudaStream_t stream);
 cudaError_t launch_resample_bank(
     const BankSite* slice, uint64_t slice_first, uint64_t slice_n, uint64_t m_total, uint64_t n_total, uint64_t first_out,
     uint64_t n_out, BankSite* next, unsigned long long* errors, cudaStream_t stream);

@@ -331,6 +331,11 @@ struct StepOut {
   // event-split schedule: the particle streamed onto a surface and left Cell lookup, event code and tallies to the
   // boundary kernel (p.event == kEvCrossPending meanwhile)
   bool need_cross;
+  // generation kernels (kDeferFission): a fission computed its yield and left the secondaries to the caller, which
+  // produces them one per loop iteration from the dead parent's rng (converged with the other lanes' isotropic
+  // directions) -- fission_nuclide names the chi rows (multigroup)
+  uint32_t pending_yield;
+  int32_t fission_nuclide;
 };
 
 // event codes used only between the kernels of one event-split pass (never in records or counters)
@@ -354,7 +359,7 @@ __device__ __forceinline__ double material_micro_total(const WorldView& w, int32
 
 // Multigroup::Interact and its Capture/Scatter/Fission (Multigroup.cpp:49-73,
 // 245-287) after Particle::SampleNuclide (Particle.cpp:110-124).
-template <bool kDeferDirection>
+template <bool kDeferDirection, bool kDeferFission = false>
 __device__ inline void collide_multigroup(
     const WorldView& w, Particle& p, int32_t mat, double micro_total, SiteDeque& dq, StepOut& out) {
   const int32_t G = w.h->n_groups;
@@ -424,6 +429,11 @@ __device__ inline void collide_multigroup(
     p.event = MMC_EV_FISSION;
     const double nubar = w.at<double>(w.h->off_mg_nubar)[nuc * G + gi];
     const uint64_t yield = static_cast<uint64_t>(__dadd_rn(nubar, p.rng.canonical()));
+    if (kDeferFission) {
+      out.pending_yield = static_cast<uint32_t>(yield);
+      out.fission_nuclide = nuc;
+      return;
+    }
     const double* chi = w.at<double>(w.h->off_mg_chi) + (static_cast<size_t>(nuc) * G + gi) * G;
     // Secondaries are spliced to the FRONT of the bank in creation order
     // (Bank.cpp:5-8).  Each one is pushed in front of the previous one, then
@@ -510,13 +520,15 @@ __device__ __forceinline__ void finish_crossing(const WorldView& w, Particle& p,
 }
 
 template <int kTracking, bool kCE, bool kDeferDirection = false, bool kDeferTsl = false, bool kPerturb = false,
-          bool kDeferCross = false>
+          bool kDeferCross = false, bool kDeferFission = false>
 __device__ __forceinline__ void transport_step(
     const WorldView& w, Particle& p, SiteDeque& dq, StepOut& out, const PerturbContext* pc = nullptr) {
   out.secondaries = 0;
   out.need_direction = false;
   out.need_tsl = false;
   out.need_cross = false;
+  out.pending_yield = 0;
+  out.fission_nuclide = -1;
   out.error_physics = out.error_capacity = out.error_lost = false;
   const int32_t mat = w.at<int32_t>(w.h->off_cell_material)[p.cell];
   if (mat < 0) {  // born in a void cell: the reference dereferences a null Material
@@ -580,8 +592,8 @@ __device__ __forceinline__ void transport_step(
     if (kPerturb) perturb_stream(w, *pc, mat, majorant, d_coll);
     stream(p, d_coll);
     if (real) {
-      if (kCE) ce::collide_continuous<kDeferTsl>(w, p, mat, dq, out, ev);
-      else collide_multigroup<kDeferDirection>(w, p, mat, micro, dq, out);
+      if (kCE) ce::collide_continuous<kDeferTsl, kDeferFission>(w, p, mat, dq, out, ev);
+      else collide_multigroup<kDeferDirection, kDeferFission>(w, p, mat, micro, dq, out);
     } else {
       p.event = MMC_EV_VIRTUAL_COLLISION;
     }
