@@ -176,6 +176,27 @@ int mmc_comm_create(int nranks, int rank, const void* id, int device, mmc_comm**
       return fail(MMC_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
     }
   }
+  if (nranks > 1) {
+    // NCCL sets its channels up lazily, at the first collective and at the first send / receive between each ordered
+    // pair of ranks (measured on B200s: 470 ms at the first exchange, 150 ms the first time a pair exchanged in the
+    // other direction): make every connection now, not inside a generation's exchange step
+    const NcclApi& api = nccl();
+    ncclResult_t r = api.AllGather(c->d_words, c->d_words + 2, 2, ncclUint64, c->comm, c->stream);
+    if (r == ncclSuccess) r = api.GroupStart();
+    for (int peer = 0; peer < nranks && r == ncclSuccess; peer++) {
+      if (peer == rank) continue;
+      r = api.Send(c->d_words, 8, ncclChar, peer, c->comm, c->stream);
+      if (r == ncclSuccess) r = api.Recv(c->d_words + 2 + 2 * peer, 8, ncclChar, peer, c->comm, c->stream);
+    }
+    if (r == ncclSuccess) r = api.GroupEnd();
+    if (r == ncclSuccess) r = api.AllReduce(c->d_words, c->d_words, 2, ncclUint64, ncclSum, c->comm, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    if (r != ncclSuccess || e != cudaSuccess) {
+      mmc_comm_destroy(c);
+      return fail(MMC_ERR_CUDA, std::string("mmc_comm_create (connection warm-up): ") +
+                                    (r != ncclSuccess ? api.GetErrorString(r) : cudaGetErrorString(e)));
+    }
+  }
   *out = c;
   return MMC_OK;
 }

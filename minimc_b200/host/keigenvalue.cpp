@@ -26,6 +26,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -116,8 +118,15 @@ EstimatorSet KEigenvalue::Solve() {
   std::vector<uint64_t> counts(P), statuses(P);
   Check(mmc_device_read(w, &counters, d_counters, sizeof(counters)), "mmc_device_read");  // (synchronises: the source bank is sampled)
   auto t_begin = std::chrono::steady_clock::now(), t_active = t_begin;
+  // MMC_K_TRACE=1: host time of every phase of every cycle on stderr (each phase ended by a device synchronisation)
+  const bool trace = std::getenv("MMC_K_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
   for (uint64_t cycle = 0; cycle < last_active; cycle++) {
     const bool score = cycle >= last_inactive;
+    const auto t0 = now();
     if (cycle == last_inactive) t_active = std::chrono::steady_clock::now();  // (the previous cycle ended with a synchronisation)
     Check(mmc_generation_run(
               w, bank_source.as<mmc_site>(), n_local, estimators.data(), static_cast<int32_t>(estimators.size()), score ? 1 : 0,
@@ -125,6 +134,7 @@ EstimatorSet KEigenvalue::Solve() {
               d_k_collision.as<uint64_t>() + cycle),
           "mmc_generation_run");
     Check(mmc_device_read(w, &counters, d_counters, sizeof(counters)), "mmc_device_read");
+    const auto t1 = now();  // (mmc_device_read synchronised: the generation and the ordering of its bank are done)
     // what this rank saw; decided alike on every rank after the all-gather below
     const uint64_t status = (counters.n_lost ? 1u : 0u) | (counters.n_physics_errors ? 2u : 0u) | (counters.n_capacity_overflow ? 4u : 0u);
     uint64_t M = 0, slice_first = 0, slice_n = 0;
@@ -136,6 +146,7 @@ EstimatorSet KEigenvalue::Solve() {
       Check(mmc_device_read(w, &counts[0], d_n_out.as<uint64_t>(), sizeof(uint64_t)), "mmc_device_read");
       statuses[0] = status;
     }
+    const auto t2 = now();
     uint64_t any = 0;
     for (uint64_t r = 0; r < P; r++) {
       M += counts[r];
@@ -155,6 +166,12 @@ EstimatorSet KEigenvalue::Solve() {
     else
       Check(mmc_bank_resample(w, bank_fission.as<mmc_site>(), 0, M, M, N, 0, N, &run_options, bank_source.as<mmc_site>(), d_errors),
             "mmc_bank_resample");
+    if (trace) {
+      uint64_t dummy = 0;
+      Check(mmc_device_read(w, &dummy, d_n_out.as<uint64_t>(), sizeof(dummy)), "mmc_device_read");  // synchronise
+      std::fprintf(stderr, "[rank %d] cycle %llu: generation %.3f ms, exchange (host view) %.3f ms, resample + pieces %.3f ms, M %llu\n",
+                   rank, static_cast<unsigned long long>(cycle), ms(t0, t1), ms(t1, t2), ms(t2, now()), static_cast<unsigned long long>(M));
+    }
   }
   // tallies, counters, resampling errors and the collision estimator's sums: one all-reduce each buffer
   if (P > 1) {
