@@ -49,8 +49,12 @@ typedef enum mmc_event {
   MMC_EV_SURFACE_CROSS = 4, MMC_EV_LEAK = 5, MMC_EV_VIRTUAL_COLLISION = 6
 } mmc_event;
 /* RNG stream.  MINSTD_COMPAT reproduces std::minstd_rand consumed through
- * libstdc++ 13 <random> (BasicTypes.hpp:27) bit for bit; the
- * counter-based mode is statistically equivalent only. */
+ * libstdc++ 13 <random> (BasicTypes.hpp:27) bit for bit.  COUNTER gives every particle its own
+ * counter-based stream (Philox-2x32-10: draw n of stream id is one block of 64 bits, no sequential state): the
+ * stream of a source particle is the one its history's seed names, a secondary's id is 64 bits drawn from its parent
+ * -- statistically equivalent to MINSTD_COMPAT (other random numbers), and like it independent of batch splits,
+ * schedules and GPU counts.  In COUNTER mode mmc_site.seed / .reserved hold the low / high word of the stream id and
+ * mmc_event_record.rng_state = (id low word << 32) | draws made. */
 typedef enum mmc_rng_mode { MMC_RNG_MINSTD_COMPAT = 0, MMC_RNG_COUNTER = 1 } mmc_rng_mode;
 /* Source.cpp:44-58 */
 typedef enum mmc_direction_kind { MMC_DIR_CONSTANT = 0, MMC_DIR_ISOTROPIC = 1, MMC_DIR_ISOTROPIC_FLUX = 2 } mmc_direction_kind;
@@ -443,7 +447,8 @@ int mmc_trace_histories(
  * log (fn 0: out0), sincos (fn 1: out0 = sin, out1 = cos), sin (fn 2), cos
  * (fn 3), the converged pair used for Direction(d, mu, phi) (fn 5: out0 = sin(x), out1 = cos(x) as two separate
  * libm calls return them) -- and the libstdc++ generate_canonical stream (fn 4: x[i] is a seed,
- * out0[i] the first canonical double of std::minstd_rand{seed}).  HOST buffers. */
+ * out0[i] the first canonical double of std::minstd_rand{seed}; fn 16 + 4: the same of the MMC_RNG_COUNTER build, the
+ * first canonical double of the Philox-2x32-10 stream whose id is x[i]).  HOST buffers. */
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n);
 
 /* Diagnostic (the reference's test_World.cpp / test_Cell.cpp / test_CSGSurface.cpp cases run through it): for each

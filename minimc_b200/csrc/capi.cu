@@ -17,10 +17,20 @@
 #include <cuda_runtime.h>
 
 #include "../../include/minimc_b200.h"
+#define MMC_DECLARE_BOTH_VARIANTS  // the launch functions of both RNG modes: mmc::lcg::*, mmc::ctr::*
 #include "kernels.h"
 #include "world_blob.h"
 
 using namespace mmc;
+// the launch functions that do not touch a generator are taken from the minstd build
+using mmc::lcg::bank_scan_blocks;
+using mmc::lcg::event_kernels_per_pass;
+using mmc::lcg::launch_evaluate_rows;
+using mmc::lcg::launch_expand_dense;
+using mmc::lcg::launch_order_bank;
+using mmc::lcg::launch_test_geometry;
+// fn(args) of the RNG mode's build
+#define MMC_BY_RNG(counter_, fn_, ...) ((counter_) ? mmc::ctr::fn_(__VA_ARGS__) : mmc::lcg::fn_(__VA_ARGS__))
 
 namespace {
 
@@ -345,6 +355,7 @@ struct Prepared {
   std::vector<double> bounds;
   LaunchConfig cfg{};
   cudaStream_t stream = nullptr;
+  bool counter_rng = false;     // MMC_RNG_COUNTER: the kernels of the Philox build (mmc::ctr)
   bool profile = false;         // time every kernel of the event-split schedule with CUDA events
   bool event_schedule = false;  // event-split kernels (event_loop.cu) instead of the fused kernel
   uint32_t event_slots = 0;     // histories in flight at once
@@ -369,8 +380,12 @@ int prepare_run(
   }
   if (opt.tracking != MMC_TRACK_SURFACE && opt.tracking != MMC_TRACK_CELL_DELTA)
     return fail(MMC_ERR_INVALID, "unknown tracking %d", opt.tracking);
-  if (opt.rng_mode != MMC_RNG_MINSTD_COMPAT)
-    return fail(MMC_ERR_INVALID, "rng_mode %d is not available in this build", opt.rng_mode);
+  if (opt.rng_mode != MMC_RNG_MINSTD_COMPAT && opt.rng_mode != MMC_RNG_COUNTER)
+    return fail(MMC_ERR_INVALID, "unknown rng_mode %d", opt.rng_mode);
+  out.counter_rng = opt.rng_mode == MMC_RNG_COUNTER;
+  if (const char* env = std::getenv("MMC_RNG_MODE")) {  // development override: "counter" / "minstd"
+    if (!options || options->rng_mode == MMC_RNG_MINSTD_COMPAT) out.counter_rng = std::strcmp(env, "counter") == 0;
+  }
   RunSpec& run = out.run;
   // source
   for (int i = 0; i < 3; i++) run.source.position[i] = source->position[i];
@@ -423,7 +438,8 @@ int prepare_run(
   // continuous-energy tables are read through the read-only global path (L2-resident)
   run.world_in_smem = (!trace && !continuous_energy && w->blob_bytes <= 96 * 1024) ? 1 : 0;
   // launch shape
-  int per_sm = max_blocks_per_sm(run.tracking, continuous_energy, generation, run.world_in_smem ? run.world_bytes : 0);
+  int per_sm = MMC_BY_RNG(out.counter_rng, max_blocks_per_sm, run.tracking, continuous_energy, generation,
+                          run.world_in_smem ? run.world_bytes : 0);
   if (per_sm < 1) per_sm = 1;
   if (opt.blocks_per_sm && static_cast<int>(opt.blocks_per_sm) < per_sm) per_sm = opt.blocks_per_sm;
   long long blocks = static_cast<long long>(w->sm_count) * per_sm;
@@ -488,7 +504,8 @@ int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
   take(st.px, n * 8), take(st.py, n * 8), take(st.pz, n * 8);
   take(st.dx, n * 8), take(st.dy, n * 8), take(st.dz, n * 8);
   take(st.energy, n * 8), take(st.tsl_T, n * 8);
-  take(st.rng, n * 4), take(st.cell, n * 4), take(st.surface, n * 4), take(st.event, n * 4);
+  take(st.rng, n * 4), take(st.rng_k0, n * 4), take(st.rng_k1, n * 4);
+  take(st.cell, n * 4), take(st.surface, n * 4), take(st.event, n * 4);
   take(st.n_pending, n * 4), take(st.dq_head, n * 4), take(st.dq_count, n * 4), take(st.tsl_off, n * 4);
   take(out.q.alive[0], n * 4), take(out.q.alive[1], n * 4), take(out.q.tsl, n * 4), take(out.q.boundary, n * 4);
   take(out.q.count, 256);
@@ -508,8 +525,8 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
   MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), p.stream));
   EventTslConfig tsl;
-  MMC_CUDA(configure_event_tsl(w->header.sc_arena_bytes, w->smem_optin, static_cast<uint32_t>(w->sm_count), tsl));
-  MMC_CUDA(launch_event_init(b.st, b.q, p.event_slots, b.counter_replicas, p.stream));
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, configure_event_tsl, w->header.sc_arena_bytes, w->smem_optin, static_cast<uint32_t>(w->sm_count), tsl));
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_event_init, b.st, b.q, p.event_slots, b.counter_replicas, p.stream));
   uint32_t alive = p.event_slots, pass = 0;
   w->last_launches = 1;
   // profile mode: CUDA events around every kernel of every pass (flight | S(a,b)), summed after the run
@@ -531,7 +548,7 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
       cudaEvent_t inner[2] = {nullptr, nullptr};
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
       if (p.profile) inner[0] = mark(), inner[1] = mark();
-      const cudaError_t err = launch_event_pass(
+      const cudaError_t err = MMC_BY_RNG(p.counter_rng, launch_event_pass,
           w->d_blob, w->header, p.run, w->d_bounds, b.st, b.q, pass, alive, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
           b.counter_replicas, tsl, p.stream, p.profile && inner[0] && inner[1] ? inner : nullptr);
       if (cudaEvent_t e = mark()) cudaEventRecord(e, p.stream);
@@ -556,8 +573,8 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
       cfg.blocks = static_cast<int>((alive + kThreadsPerBlock - 1) / kThreadsPerBlock);
       RunSpec run = p.run;
       run.chunk = 32;
-      err = launch_fixed_source(cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending, w->d_next, d_scores, d_square,
-                                d_counters, nullptr, p.stream, &resume);
+      err = MMC_BY_RNG(p.counter_rng, launch_fixed_source, cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
+                       d_scores, d_square, d_counters, nullptr, p.stream, &resume);
       if (err != cudaSuccess) status = fail(MMC_ERR_CUDA, "hand-over to the fused kernel: %s", cudaGetErrorString(err));
       w->last_launches += 1;
       alive = 0;
@@ -572,7 +589,7 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
   }
   for (cudaEvent_t e : marks) cudaEventDestroy(e);
   if (status != MMC_OK) return status;
-  MMC_CUDA(launch_event_finish(b.counter_replicas, d_counters, p.stream));
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_event_finish, b.counter_replicas, d_counters, p.stream));
   w->last_launches += 1;
   return MMC_OK;
 }
@@ -1068,7 +1085,7 @@ int mmc_fixed_source_run_device(
   if (!p.bounds.empty())
     MMC_CUDA(cudaMemcpyAsync(w->d_bounds, p.bounds.data(), p.bounds.size() * sizeof(double), cudaMemcpyHostToDevice, p.stream));
   MMC_CUDA(cudaMemsetAsync(w->d_next, 0, sizeof(unsigned long long), p.stream));
-  MMC_CUDA(launch_fixed_source(
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_fixed_source,
       p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
       reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,
       nullptr, p.stream));
@@ -1086,7 +1103,7 @@ int mmc_source_bank_sample(const mmc_world* world, const mmc_source_desc* source
   if (int s = prepare_run(w, source, nullptr, 0, seed0, first_index, n, options, true, p)) return s;
   if (n && !d_bank) return fail(MMC_ERR_INVALID, "d_bank is NULL");
   MMC_CUDA(cudaSetDevice(w->device));
-  MMC_CUDA(launch_source_bank(p.run, reinterpret_cast<BankSite*>(d_bank), p.stream));
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_source_bank, p.run, reinterpret_cast<BankSite*>(d_bank), p.stream));
   return MMC_OK;
 }
 
@@ -1148,7 +1165,7 @@ int mmc_generation_run(const mmc_world* world, const mmc_site* d_bank_in, uint64
   io.child_count = w->d_child_count;
   io.child_start = w->d_child_start;
   io.k_collision = reinterpret_cast<unsigned long long*>(d_k_collision);
-  MMC_CUDA(launch_fixed_source(
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_fixed_source,
       p.cfg, w->d_blob, p.run, w->d_bounds, w->d_sites, w->d_pending, w->d_next,
       reinterpret_cast<unsigned long long*>(d_scores), reinterpret_cast<unsigned long long*>(d_square_scores), d_counters,
       &io, p.stream));
@@ -1168,7 +1185,9 @@ int mmc_bank_resample(const mmc_world* world, const mmc_site* d_slice, uint64_t 
   if (options && options->struct_size != sizeof(mmc_run_options)) return fail(MMC_ERR_INVALID, "mmc_run_options ABI mismatch");
   MMC_CUDA(cudaSetDevice(world->device));
   cudaStream_t stream = options && options->stream ? static_cast<cudaStream_t>(options->stream) : world->stream;
-  MMC_CUDA(launch_resample_bank(
+  const bool counter_rng = (options && options->rng_mode == MMC_RNG_COUNTER) ||
+                           (std::getenv("MMC_RNG_MODE") && std::strcmp(std::getenv("MMC_RNG_MODE"), "counter") == 0);
+  MMC_CUDA(MMC_BY_RNG(counter_rng, launch_resample_bank,
       reinterpret_cast<const BankSite*>(d_slice), slice_first, slice_n, m_total, n_total, first_out, n_out,
       reinterpret_cast<BankSite*>(d_bank_next), reinterpret_cast<unsigned long long*>(d_errors), stream));
   return MMC_OK;
@@ -1221,7 +1240,8 @@ int mmc_fixed_source_run_sensitivities(
   MMC_CUDA(cudaSetDevice(w->device));
   if (n_histories == 0) return MMC_OK;
   // launch shape of the kPerturb instantiation
-  int per_sm = max_blocks_per_sm(run.tracking, run.continuous_energy != 0, false, run.world_in_smem ? run.world_bytes : 0, true);
+  int per_sm = MMC_BY_RNG(p.counter_rng, max_blocks_per_sm, run.tracking, run.continuous_energy != 0, false,
+                          run.world_in_smem ? run.world_bytes : 0, true);
   if (per_sm < 1) per_sm = 1;
   long long blocks = static_cast<long long>(w->sm_count) * per_sm;
   const long long useful = static_cast<long long>((n_histories + kThreadsPerBlock - 1) / kThreadsPerBlock);
@@ -1262,8 +1282,8 @@ int mmc_fixed_source_run_sensitivities(
   auto* d_tally = reinterpret_cast<unsigned long long*>(w->d_sens + 2 * sens_bins);
   auto* d_counters = reinterpret_cast<mmc_counters*>(d_tally + 2 * total_bins);
   w->last_launches = 1;
-  MMC_CUDA(launch_fixed_source(p.cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending, w->d_next, d_tally,
-                               d_tally + total_bins, d_counters, nullptr, stream, nullptr, &io));
+  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_fixed_source, p.cfg, w->d_blob, run, w->d_bounds, w->d_sites, w->d_pending,
+                      w->d_next, d_tally, d_tally + total_bins, d_counters, nullptr, stream, nullptr, &io));
   MMC_CUDA(cudaMemcpyAsync(w->h_sens, w->d_sens, words * sizeof(double), cudaMemcpyDeviceToHost, stream));
   MMC_CUDA(cudaStreamSynchronize(stream));
   for (uint64_t i = 0; i < sens_bins; i++) {
@@ -1351,7 +1371,7 @@ int mmc_trace_histories(
   if (e == cudaSuccess) e = cudaMalloc(&d_counters, sizeof(mmc_counters));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_counters, 0, sizeof(mmc_counters), p.stream);
   if (e == cudaSuccess)
-    e = launch_trace(w->d_blob, p.run, w->d_sites, d_records, cap, d_n, d_counters, p.stream);
+    e = MMC_BY_RNG(p.counter_rng, launch_trace, w->d_blob, p.run, w->d_sites, d_records, cap, d_n, d_counters, p.stream);
   unsigned long long n = 0;
   mmc_counters h_counters{};
   if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, p.stream);
@@ -1435,7 +1455,7 @@ int mmc_test_geometry(const mmc_world* world, size_t n, const double* positions,
 }
 
 int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, size_t n) {
-  if (fn < 0 || fn > 5 || !x || !out0 || ((fn == 1 || fn == 5) && !out1)) return fail(MMC_ERR_INVALID, "bad arguments");
+  if (fn < 0 || (fn > 5 && fn != 16 + 4) || !x || !out0 || ((fn == 1 || fn == 5) && !out1)) return fail(MMC_ERR_INVALID, "bad arguments");
   if (mmc_device_count() < 1) return fail(MMC_ERR_NO_DEVICE, "no CUDA device visible");
   if (n == 0) return MMC_OK;
   double *d_x = nullptr, *d_0 = nullptr, *d_1 = nullptr;
@@ -1443,7 +1463,7 @@ int mmc_test_device_math(int fn, const double* x, double* out0, double* out1, si
   if (e == cudaSuccess) e = cudaMalloc(&d_0, n * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_1, n * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = launch_test_math(fn, d_x, d_0, d_1, n, nullptr);
+  if (e == cudaSuccess) e = fn >= 16 ? mmc::ctr::launch_test_math(fn - 16, d_x, d_0, d_1, n, nullptr) : mmc::lcg::launch_test_math(fn, d_x, d_0, d_1, n, nullptr);
   if (e == cudaSuccess) e = cudaMemcpy(out0, d_0, n * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && (fn == 1 || fn == 5)) e = cudaMemcpy(out1, d_1, n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d_x);

@@ -64,8 +64,31 @@
 #endif
 
 namespace mmc {
+namespace MMC_VARIANT_NS {  // lcg or ctr: this file is compiled once per RNG mode (kernels.h)
 
 namespace {
+
+// a slot's generator: the minstd state, or (counter mode) the draws made and the stream's id
+__device__ __forceinline__ Rng load_rng(const EventState& st, uint32_t slot) {
+  Rng r;
+  r.x = MMC_LD(st.rng[slot]);
+#if MMC_COUNTER_RNG
+  r.k0 = MMC_LD(st.rng_k0[slot]);
+  r.k1 = MMC_LD(st.rng_k1[slot]);
+#endif
+  return r;
+}
+// kStream: the particle may be a new one (births in the boundary work); a flight or a scatter keeps its stream
+template <bool kStream>
+__device__ __forceinline__ void store_rng(const EventState& st, uint32_t slot, const Rng& r) {
+  MMC_ST(st.rng[slot], r.x);
+#if MMC_COUNTER_RNG
+  if (kStream) {
+    MMC_ST(st.rng_k0[slot], r.k0);
+    MMC_ST(st.rng_k1[slot], r.k1);
+  }
+#endif
+}
 
 constexpr int kFlightThreads = MMC_EV_FLIGHT_THREADS;
 constexpr int kWarpsPerBlock = kFlightThreads / 32;
@@ -95,7 +118,7 @@ __global__ void event_init_kernel(const __grid_constant__ EventState st, const _
     st.event[i] = MMC_EV_CAPTURE;  // "dead": the first pass refills every slot
     // the flight kernel loads a slot's particle together with its event code, before it knows the slot is dead
     st.px[i] = st.py[i] = st.pz[i] = st.dx[i] = st.dy[i] = st.dz[i] = st.energy[i] = st.tsl_T[i] = 0.0;
-    st.rng[i] = 0;
+    st.rng[i] = st.rng_k0[i] = st.rng_k1[i] = 0;
     st.cell[i] = st.surface[i] = -1;
     st.tsl_off[i] = 0;
     st.n_pending[i] = 0;
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
   p.energy = MMC_LD(st.energy[slot]);
   p.group = 0;
-  p.rng.x = MMC_LD(st.rng[slot]);
+  p.rng = load_rng(st, slot);
   p.cell = MMC_LD(st.cell[slot]);
   p.surface = -1;  // written only by a crossing; tallies read it in the boundary kernel
   if (blockIdx.x == 0 && threadIdx.x == 0) q.count[4] = q.count[7] = 0;  // chunk counters of this pass's S(a,b) kernel
@@ -234,7 +257,7 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
     MMC_ST(st.px[slot], p.px), MMC_ST(st.py[slot], p.py), MMC_ST(st.pz[slot], p.pz);
     MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
     MMC_ST(st.energy[slot], p.energy);
-    MMC_ST(st.rng[slot], p.rng.x);
+    store_rng<false>(st, slot, p.rng);
     MMC_ST(st.event[slot], p.event);
     if (o.need_cross) MMC_ST(st.surface[slot], p.surface);
     if (has_secondaries) {
@@ -295,7 +318,7 @@ __device__ __forceinline__ void boundary_chunk(
   p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
   p.energy = MMC_LD(st.energy[slot]);
   p.group = 0;
-  p.rng.x = MMC_LD(st.rng[slot]);
+  p.rng = load_rng(st, slot);
   p.cell = MMC_LD(st.cell[slot]);
   p.surface = MMC_LD(st.surface[slot]);
   uint32_t n_pending = run.n_estimators ? MMC_LD(st.n_pending[slot]) : 0u;
@@ -396,7 +419,7 @@ __device__ __forceinline__ void boundary_chunk(
     MMC_ST(st.px[slot], p.px), MMC_ST(st.py[slot], p.py), MMC_ST(st.pz[slot], p.pz);
     MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
     MMC_ST(st.energy[slot], p.energy);
-    MMC_ST(st.rng[slot], p.rng.x);
+    store_rng<true>(st, slot, p.rng);
     MMC_ST(st.cell[slot], p.cell);
     MMC_ST(st.surface[slot], p.surface);
     MMC_ST(st.event[slot], p.event);
@@ -537,7 +560,7 @@ __global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslTh
     const uint32_t slot = q.tsl[i];
     Particle p;
     p.energy = MMC_LD(st.energy[slot]);
-    p.rng.x = MMC_LD(st.rng[slot]);
+    p.rng = load_rng(st, slot);
     const double T = MMC_LD(st.tsl_T[slot]);
     const TslTable& t = *w.at<TslTable>(MMC_LD(st.tsl_off[slot]));
     bool error = false;
@@ -550,7 +573,7 @@ __global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslTh
       MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
       MMC_ST(st.energy[slot], p.energy);
     }
-    MMC_ST(st.rng[slot], p.rng.x);
+    store_rng<false>(st, slot, p.rng);
     if (error) {
       // the reference throws here (-> std::terminate); the flight kernel counted the collision already
       MMC_ST(st.event[slot], MMC_EV_CAPTURE);
@@ -639,4 +662,5 @@ cudaError_t launch_event_finish(const unsigned long long* counter_replicas, mmc_
   return cudaGetLastError();
 }
 
+}  // namespace MMC_VARIANT_NS
 }  // namespace mmc

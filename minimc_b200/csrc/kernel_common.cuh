@@ -21,7 +21,7 @@ __device__ __forceinline__ void load_site(const BankSite& s, Particle& p) {
   p.dz = s.direction[2];
   p.group = s.energy_bits;
   p.energy = __longlong_as_double(static_cast<long long>(s.energy_bits));
-  p.rng.x = lcg_seed(s.seed);
+  p.rng = Rng::seeded(load_seed(s));
   p.cell = -1;
   p.surface = -1;
   p.event = MMC_EV_BIRTH;

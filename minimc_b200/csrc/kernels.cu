@@ -34,6 +34,7 @@
 #endif
 
 namespace mmc {
+namespace MMC_VARIANT_NS {  // lcg or ctr: this file is compiled once per RNG mode (kernels.h)
 
 namespace {
 
@@ -125,6 +126,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
     p.energy = st.energy[scratch];
     p.group = 0;
     p.rng.x = st.rng[scratch];
+#if MMC_COUNTER_RNG
+    p.rng.k0 = st.rng_k0[scratch], p.rng.k1 = st.rng_k1[scratch];
+#endif
     p.cell = st.cell[scratch];
     p.surface = st.surface[scratch];
     if (run.n_estimators) n_pending = st.n_pending[scratch];
@@ -239,8 +243,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM :
             s.position[0] = p.px, s.position[1] = p.py, s.position[2] = p.pz;
             s.direction[0] = ix, s.direction[1] = iy, s.direction[2] = iz;
             s.energy_bits = kCE ? static_cast<uint64_t>(__double_as_longlong(p.energy)) : child_group;
-            s.seed = p.rng.raw();  // Particle::BankSecondaries, Particle.cpp:96-100
-            s.surface = -1;
+            store_seed(s, p.rng.spawn());  // Particle::BankSecondaries, Particle.cpp:96-100
             bank.out[site_start + sites_made] = s;
             sites_made++;
           } else {
@@ -422,7 +425,7 @@ __global__ void trace_kernel(
       r.direction[0] = p.dx;
       r.direction[1] = p.dy;
       r.direction[2] = p.dz;
-      r.rng_state = p.rng.x;
+      r.rng_state = p.rng.state64();
     }
     n++;
   };
@@ -481,7 +484,7 @@ __global__ void test_math_kernel(int fn, const double* x, double* out0, double* 
   } else if (fn == 5) {
     glibc::sin_and_cos(x[i], &out0[i], &out1[i]);
   } else {
-    Rng rng{lcg_seed(static_cast<uint64_t>(x[i]))};
+    Rng rng = Rng::seeded(static_cast<uint64_t>(x[i]));
     out0[i] = rng.canonical();
   }
 }
@@ -498,8 +501,7 @@ __global__ void source_bank_kernel(const __grid_constant__ RunSpec run, BankSite
   s.position[0] = p.px, s.position[1] = p.py, s.position[2] = p.pz;
   s.direction[0] = p.dx, s.direction[1] = p.dy, s.direction[2] = p.dz;
   s.energy_bits = run.continuous_energy ? static_cast<uint64_t>(__double_as_longlong(p.energy)) : p.group;
-  s.seed = p.rng.x;
-  s.surface = -1;
+  store_seed(s, p.rng.stream());  // the particle's generator has made no draw yet: its seed is its state
   bank[i] = s;
 }
 
@@ -610,8 +612,7 @@ __global__ void resample_bank_kernel(
     return;
   }
   BankSite s = slice[j - slice_first];
-  s.seed = static_cast<uint32_t>(static_cast<uint64_t>(s.seed) + (i - i0));
-  s.surface = -1;
+  store_seed(s, load_seed(s) + (i - i0));  // (minstd mode: the sum wraps to 32 bits, as the seed word does)
   next[t] = s;
 }
 
@@ -803,4 +804,5 @@ int max_blocks_per_sm(int tracking, bool continuous_energy, bool generation, siz
   });
 }
 
+}  // namespace MMC_VARIANT_NS
 }  // namespace mmc

@@ -50,6 +50,60 @@ __host__ __device__ __forceinline__ uint32_t lcg_next(uint32_t x) {
   return r >= kLcgM ? r - kLcgM : r;
 }
 
+#ifndef MMC_COUNTER_RNG
+#define MMC_COUNTER_RNG 0
+#endif
+
+#if MMC_COUNTER_RNG
+// MMC_COUNTER_RNG = 1 (mmc_rng_mode MMC_RNG_COUNTER of include/minimc_b200.h; this translation unit is compiled once per mode): a
+// counter-based generator per particle instead of the reference's sequential std::minstd_rand -- Philox-2x32-10
+// (Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11; restated from the paper).  A
+// stream is a 64-bit id (the Philox key and the high word of its counter); draw number n of the stream is the block
+// philox(key = id.lo, counter = (n, id.hi)) -- 64 fresh bits, no state to advance, no division in canonical().  Where
+// the reference constructs a generator from a seed (Source::Sample's std::minstd_rand{seed + i}, the Particle ctor's
+// rng{seed}, Particle::BankSecondaries' seed = parent's next draw, Source.cpp:143-154, Particle.cpp:96-100) this mode
+// starts the stream whose id is that seed, taken as the 64 bits of one block.  Results are statistically equivalent
+// to the minstd mode (not bit-identical: other random numbers) and, like it, independent of batch splits, schedules
+// and GPU counts: a particle's stream is a pure function of its history's seed and its ancestry.
+struct Rng {
+  uint32_t x;       // draws made so far (the counter's low word)
+  uint32_t k0, k1;  // the stream's 64-bit id
+  __device__ __forceinline__ uint2 block() {
+    uint32_t c0 = x, c1 = k1, key = k0;
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+      const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+      c0 = hi ^ key ^ c1;
+      c1 = lo;
+      key += 0x9E3779B9u;
+    }
+    x++;
+    return make_uint2(c0, c1);
+  }
+  __device__ __forceinline__ uint32_t raw() { return block().x; }
+  // 53 random bits scaled to [0, 1): every value is a multiple of 2^-53 below 1
+  __device__ __forceinline__ double canonical() {
+    const uint2 b = block();
+    const uint64_t bits = (static_cast<uint64_t>(b.x) << 32 | b.y) >> 11;
+    return __dmul_rn(static_cast<double>(bits), 1.1102230246251565404e-16);
+  }
+  // the seed handed to a new generator (Particle ctor, BankSecondaries): 64 bits
+  __device__ __forceinline__ uint64_t spawn() {
+    const uint2 b = block();
+    return static_cast<uint64_t>(b.x) << 32 | b.y;
+  }
+  __device__ __forceinline__ static Rng seeded(uint64_t seed) {
+    Rng r;
+    r.x = 0;
+    r.k0 = static_cast<uint32_t>(seed);
+    r.k1 = static_cast<uint32_t>(seed >> 32);
+    return r;
+  }
+  __device__ __forceinline__ uint64_t stream() const { return static_cast<uint64_t>(k1) << 32 | k0; }
+  // for event records: the stream's low word and the draws made
+  __device__ __forceinline__ uint64_t state64() const { return static_cast<uint64_t>(k0) << 32 | x; }
+};
+#else
 struct Rng {
   uint32_t x;
   __device__ __forceinline__ uint32_t raw() {
@@ -68,7 +122,24 @@ struct Rng {
     if (u >= 1.0) u = 0.99999999999999988897769753748;  // nextafter(1, 0)
     return u;
   }
+  // the seed handed to a new generator (Particle ctor, BankSecondaries): the engine's next 32-bit output
+  __device__ __forceinline__ uint64_t spawn() { return raw(); }
+  // std::minstd_rand{seed}
+  __device__ __forceinline__ static Rng seeded(uint64_t seed) { return Rng{lcg_seed(seed)}; }
+  __device__ __forceinline__ uint64_t stream() const { return x; }
+  __device__ __forceinline__ uint64_t state64() const { return x; }
 };
+#endif
+
+// A generator's seed in a bank site: the 32-bit seed of std::minstd_rand{seed} (Particle.cpp:96-100), or, in counter
+// mode, the stream's 64-bit id in the seed and surface words (Particle::current_surface of a banked particle is null).
+__device__ __forceinline__ void store_seed(BankSite& s, uint64_t seed) {
+  s.seed = static_cast<uint32_t>(seed);
+  s.surface = MMC_COUNTER_RNG ? static_cast<int32_t>(static_cast<uint32_t>(seed >> 32)) : -1;
+}
+__device__ __forceinline__ uint64_t load_seed(const BankSite& s) {
+  return MMC_COUNTER_RNG ? (static_cast<uint64_t>(static_cast<uint32_t>(s.surface)) << 32 | s.seed) : s.seed;
+}
 
 // ------------------------------------------------------------------ particle
 struct Particle {
@@ -272,7 +343,7 @@ __device__ __forceinline__ void stream(Particle& p, double d) {
 // stream (std::minstd_rand{seed}) and the function returns true; the caller then runs
 // isotropic_direction(p.rng, ...) followed by finish_source(p), which together are the rest of Source::Sample.
 __device__ inline bool sample_source(const SourceSpec& src, uint64_t seed, Particle& p, bool defer_isotropic = false) {
-  Rng rng{lcg_seed(seed)};
+  Rng rng = Rng::seeded(seed);
   p.px = src.position[0];
   p.py = src.position[1];
   p.pz = src.position[2];
@@ -297,12 +368,12 @@ __device__ inline bool sample_source(const SourceSpec& src, uint64_t seed, Parti
     p.dy = src.direction[1];
     p.dz = src.direction[2];
   }
-  p.rng.x = lcg_seed(rng.raw());  // Particle ctor: rng{seed}
+  p.rng = Rng::seeded(rng.spawn());  // Particle ctor: rng{seed}
   return false;
 }
 
 // auto sampled_seed = rng(); Particle{..., sampled_seed} (Source.cpp:149-153)
-__device__ __forceinline__ void finish_source(Particle& p) { p.rng.x = lcg_seed(p.rng.raw()); }
+__device__ __forceinline__ void finish_source(Particle& p) { p.rng = Rng::seeded(p.rng.spawn()); }
 
 // ------------------------------------------------------- secondary particles
 // Per-thread ring deque in global scratch reproducing the bank order of
@@ -451,8 +522,7 @@ __device__ inline void collide_multigroup(
           s.position[2] = p.pz;
           isotropic_direction(p.rng, s.direction[0], s.direction[1], s.direction[2]);
           s.energy_bits = static_cast<uint64_t>(g + 1);
-          s.seed = p.rng.raw();  // Particle::BankSecondaries, Particle.cpp:96-100
-          s.surface = -1;
+          store_seed(s, p.rng.spawn());  // Particle::BankSecondaries, Particle.cpp:96-100
           if (dq.count > dq.mask) {
             out.error_capacity = true;
           } else {
