@@ -86,6 +86,9 @@ def test_counter_mode_agrees_with_minstd_within_3_sigma(full_tables, name):
     var = (np.maximum(q0 - s0 * s0 / n, 0) + np.maximum(q1 - s1 * s1 / n, 0)) / (n * n)
     populated = (s0 + s1) >= 40  # bins with enough hits for a normal approximation
     z = (mean1 - mean0)[populated] / np.sqrt(var[populated])
+    if name.startswith("C1"):  # (nothing leaks from the sphere of radius 1e10: the event counts below are the check)
+        assert len(z) == 0 and s0.sum() == s1.sum() == 0
+        z = np.zeros(1)
     assert np.abs(z).max() < 4.5, (name, np.abs(z).max())          # no bin far out (hundreds to thousands of bins)
     assert (np.abs(z) > 3).mean() <= 0.01 + 3 / max(len(z), 1), name  # 0.27 % expected beyond 3 sigma
     assert 0.75 < (z * z).mean() < 1.3 or len(z) < 30, (name, (z * z).mean())
