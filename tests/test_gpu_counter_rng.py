@@ -89,7 +89,8 @@ def test_counter_mode_agrees_with_minstd_within_3_sigma(full_tables, name):
     if name.startswith("C1"):  # (nothing leaks from the sphere of radius 1e10: the event counts below are the check)
         assert len(z) == 0 and s0.sum() == s1.sum() == 0
         z = np.zeros(1)
-    assert np.abs(z).max() < 4.5, (name, np.abs(z).max())          # no bin far out (hundreds to thousands of bins)
+    # no bin far out: the largest of n standard normal deviates is about sqrt(2 ln n) (4.3 for broomstick's ~10^4 bins)
+    assert np.abs(z).max() < np.sqrt(2 * np.log(max(len(z), 2))) + 1.5, (name, np.abs(z).max(), len(z))
     assert (np.abs(z) > 3).mean() <= 0.01 + 3 / max(len(z), 1), name  # 0.27 % expected beyond 3 sigma
     assert 0.75 < (z * z).mean() < 1.3 or len(z) < 30, (name, (z * z).mean())
     # event counts per history agree too (3 sigma of a Poisson-like count, generously)
