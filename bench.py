@@ -323,7 +323,7 @@ def run_reference_arm_keigenvalue(args, cores):
 
 
 # --------------------------------------------------------------------- GPU arm
-def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool, total_histories=None):
+def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool, total_histories=None, rng_mode=0):
     """One fixed-source workload on this rank's GPU; returns the result dict on rank 0 (None elsewhere).
     total_histories: strong scaling (a fixed batch split over the ranks) instead of n_per_gpu per rank."""
     import torch
@@ -338,7 +338,7 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool, t
     if not strong:
         total_histories = n_per_gpu * world_size
     drv = capi.Driver(text=deck_text(workload, table_dir, total_histories, 1))
-    drv.set_options(device=local_rank)
+    drv.set_options(device=local_rank, rng_mode=rng_mode)
     first, count = distributed.shard(0, total_histories, rank, world_size)
     bins = max(drv.total_bins, 1)
     n_counters = len(capi.Counters._fields_)
@@ -391,11 +391,11 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool, t
     kernel_split = None
     if schedule == "event":
         # one more (untimed) step with CUDA events around every kernel: the flight / S(a,b) split of the device time
-        drv.set_options(device=local_rank, profile=1)
+        drv.set_options(device=local_rank, profile=1, rng_mode=rng_mode)
         step()
         sync_all()
         flight_ms, tsl_ms, boundary_ms = drv.last_kernel_ms()
-        drv.set_options(device=local_rank)
+        drv.set_options(device=local_rank, rng_mode=rng_mode)
         kernel_split = {"event_flight_kernel_ms": flight_ms, "event_tsl_kernel_ms": tsl_ms,
                         "event_boundary_kernel_ms": boundary_ms,
                         "dominant": "event_tsl_kernel" if tsl_ms >= flight_ms else "event_flight_kernel",
@@ -448,7 +448,8 @@ def measure(args, workload, n_per_gpu, steps, warmup, ctx, cpu_baseline: bool, t
         "counters_per_step": c,
         "config": {"workload": w["name"],
                    "histories_per_gpu_per_step": total_histories / world_size if strong else n_per_gpu,
-                   "histories_per_step": total_histories, "rng": "minstd_compat (bit-exact)",
+                   "histories_per_step": total_histories,
+                   "rng": "counter (Philox-2x32-10 per particle)" if rng_mode else "minstd_compat (bit-exact)",
                    "estimator_bins": int(bins), "l2": "flushed between timed steps (256 MiB write, untimed)",
                    "parallelism": f"histories sharded over {world_size} GPU(s), one all-reduce of the packed integer "
                                   f"tallies per step (mmc_tally_allreduce)"},
@@ -580,13 +581,15 @@ def run_gpu_arm(args):
         return
     strong_total = args.total_histories if args.scaling == "strong" else None
     main = measure(args, args.workload, n_per_gpu, args.steps, args.warmup, ctx, cpu_baseline=want_cpu,
-                   total_histories=strong_total)
+                   total_histories=strong_total, rng_mode=1 if args.rng == "counter" else 0)
     extra = None
     if args.workload != "multigroup_critical" and not args.no_multigroup:
         extra = measure(args, "multigroup_critical", WORKLOADS["multigroup_critical"]["histories_per_gpu"], 3, 3, ctx,
                         cpu_baseline=False)
-    small = keig = None
+    small = keig = counter = None
     if args.workload == "single_zone" and not args.no_extras and strong_total is None and not args.histories_per_gpu:
+        # the same workload with MMC_RNG_COUNTER (a Philox-2x32-10 stream per particle; statistically equivalent)
+        counter = measure(args, "single_zone", n_per_gpu, 3, 3, ctx, cpu_baseline=False, rng_mode=1)
         # the deck as shipped (benchmarks/single_zone.xml: 10^6 histories) -- a batch that ends before the GPU is full
         small = measure(args, "single_zone", 1_000_000, 5, 3, ctx, cpu_baseline=False)
         # BASELINE.json's metric names active k-eigenvalue cycles: both power iterations, briefly
@@ -614,6 +617,10 @@ def run_gpu_arm(args):
                                        "ms_per_step": small["ms_per_step"], "e2e": small["e2e"],
                                        "fraction_of_large_batch_rate": small["value"] / main["value"],
                                        "launches_per_step": small["launches_per_step"]}
+        if counter is not None:
+            line["counter_rng"] = {"rng": counter["config"]["rng"], "value": counter["value"], "unit": "histories/s",
+                                   "steps": 3, "ms_per_step": counter["ms_per_step"], "e2e": counter["e2e"],
+                                   "fraction_of_minstd_rate": counter["value"] / main["value"]}
         if keig is not None:
             line["keigenvalue"] = keig
         sys.stdout.flush()
@@ -634,6 +641,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--total-histories", type=int, default=100_000_000,
                     help="--scaling strong: the batch split over the GPUs (BASELINE configs[4]: 1e8 histories)")
+    ap.add_argument("--rng", default="minstd", choices=["minstd", "counter"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multigroup", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the 10^6-history and k-eigenvalue lines of the default run")

@@ -32,12 +32,13 @@ def _rank_counts():
     return [p for p in (2, 3, 4, 8) if p <= n]
 
 
-def _run_cli(deck: Path, nranks: int):
+def _run_cli(deck: Path, nranks: int, extra_env=None):
     """Runs the CLI on `nranks` GPUs; returns (rank 0's .out text, the cycle lines of every rank's stdout)."""
     procs = []
     id_file = deck.parent / f"nccl_id_{nranks}"
     for rank in range(nranks):
         env = dict(os.environ)
+        env.update(extra_env or {})
         if nranks > 1:
             env.update(MMC_WORLD_SIZE=str(nranks), MMC_RANK=str(rank), MMC_DEVICE=str(rank), MMC_COMM_ID_FILE=os.fspath(id_file))
         procs.append(subprocess.Popen([os.fspath(CLI), os.fspath(deck)], env=env, stdout=subprocess.PIPE,
@@ -74,20 +75,29 @@ def _cases(tables):
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs at least two GPUs")
 @pytest.mark.parametrize("name", ["mg_k_slab", "mg_k_infinite_delta", "ce_fissile_sphere_k", "mg_three_shells_fixed",
-                                  "ce_single_zone_fixed"])
+                                  "ce_single_zone_fixed", "mg_k_slab/counter", "ce_single_zone_fixed/counter"])
 def test_cli_ranks_reproduce_the_single_process_run(tables, tmp_path, name):
+    # "/counter": MMC_RNG_MODE=counter, the Philox build of every kernel (a particle's stream does not depend on the rank
+    # that runs it, so the result is the same for any number of GPUs in this mode too)
+    name, _, rng = name.partition("/")
+    extra_env = {"MMC_RNG_MODE": "counter"} if rng else None
     text = _cases(tables)[name]
     single_dir = tmp_path / "p1"
     single_dir.mkdir()
     (single_dir / "deck.xml").write_text(text)
-    ref_out, ref_lines = _run_cli(single_dir / "deck.xml", 1)
+    ref_out, ref_lines = _run_cli(single_dir / "deck.xml", 1, extra_env)
+    if rng:  # other random numbers than the minstd build
+        plain_dir = tmp_path / "p1_minstd"
+        plain_dir.mkdir()
+        (plain_dir / "deck.xml").write_text(text)
+        assert _run_cli(plain_dir / "deck.xml", 1)[0] != ref_out
     if "_k" in name:
         assert any(line.startswith("cycle ") for line in ref_lines[0])
     for nranks in _rank_counts():
         d = tmp_path / f"p{nranks}"
         d.mkdir()
         (d / "deck.xml").write_text(text)
-        out, lines = _run_cli(d / "deck.xml", nranks)
+        out, lines = _run_cli(d / "deck.xml", nranks, extra_env)
         assert out == ref_out, f"{name}: .out differs at {nranks} ranks"
         for rank_lines in lines:  # every rank prints the same k of every cycle, bank sizes and collision estimator
             assert rank_lines == ref_lines[0], f"{name}: cycle lines differ at {nranks} ranks"
