@@ -45,17 +45,7 @@ SIZES = {
 TSL_CUTOFF_ENERGY = 2.0e-6  # MeV: last point of the scatter_xs_E axis (ThermalScattering.hpp:125-126)
 
 
-def write_table(path, axes, values) -> None:
-    axes = [np.ascontiguousarray(a, np.float64) for a in axes]
-    values = np.ascontiguousarray(values, np.float64)
-    assert values.shape == tuple(len(a) for a in axes), (values.shape, [len(a) for a in axes])
-    with open(path, "wb") as f:
-        f.write(b"MMCTAB1\0")
-        f.write(struct.pack("<Q", len(axes)))
-        f.write(struct.pack(f"<{len(axes)}Q", *[len(a) for a in axes]))
-        for a in axes:
-            f.write(a.tobytes())
-        f.write(values.tobytes())
+from .mmctab import write_table  # noqa: E402,F401  (the MMCTAB1 writer lives with the converter)
 
 
 def _geometric(first: float, ratio: float, n: int) -> np.ndarray:
