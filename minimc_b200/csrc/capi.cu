@@ -846,6 +846,7 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
       std::vector<TslPartition> out(n);
       std::vector<uint32_t> tail(n, 0), tail_eval(n, 0);
       std::vector<char> expanded(n, 0), evaluated(n, 0);
+      std::vector<size_t> job_of(n, 0);  // index of partition i's EvalJob
       for (int i = 0; i < n; i++) {
         const mmc_tsl_partition& q = p[i];
         TslPartition& o = out[i];
@@ -867,9 +868,11 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           jobs.push_back(DenseJob{o.off_scaled_cdf_modes, o.off_modes, tail[i], o.n_grid, o.n_cdf, o.n_T, o.rank, 1u});
         }
         o.off_eval = 0;
+        o.eval_sorted = 0;
         if (!eval_T.empty() && q.n_temperature <= 255 &&
             reserve_tail(eval_T.size() * q.n_grid * q.n_cdf, tail_eval[i])) {
           evaluated[i] = 1;
+          o.eval_sorted = std::getenv("MMC_TSL_SORTED_SEARCH") && std::atoi(std::getenv("MMC_TSL_SORTED_SEARCH")) == 0 ? 0u : 1u;
           EvalJob job{};
           job.off_a = o.off_scaled_cdf_modes;
           job.off_m = o.off_modes;
@@ -887,13 +890,19 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
             job.dT[s] = Ts[T_hi_i] - Ts[T_lo_i];
             job.tT[s] = eval_T[s] - Ts[T_lo_i];
           }
+          job_of[i] = eval_jobs.size();
           eval_jobs.push_back(job);
         }
       }
       const uint32_t at = b.add(out.data(), out.size());
       for (int i = 0; i < n; i++) {
         if (expanded[i]) dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_dense), tail[i]});
-        if (evaluated[i]) dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_eval), tail_eval[i]});
+        if (evaluated[i]) {
+          dense_patches.push_back({at + i * sizeof(TslPartition) + offsetof(TslPartition, off_eval), tail_eval[i]});
+          // the job of this partition learns where the partition's eval_sorted flag lives
+          eval_jobs[job_of[i]].off_sorted_flag =
+              static_cast<uint32_t>(at + i * sizeof(TslPartition) + offsetof(TslPartition, eval_sorted));
+        }
       }
       return at;
     };

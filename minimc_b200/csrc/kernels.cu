@@ -665,11 +665,24 @@ __global__ void evaluate_rows_kernel(char* world, const __grid_constant__ EvalJo
       __dadd_rn(v_lo, __dmul_rn(__ddiv_rn(__dsub_rn(v_hi, v_lo), job.dT[s]), job.tT[s]));
 }
 
+// One thread per evaluated row (temperature slot, grid point): clears the partition's eval_sorted flag (set in the
+// uploaded image) when the row is not non-decreasing -- NaN included -- in the CDF node.
+__global__ void check_rows_sorted_kernel(char* world, const __grid_constant__ EvalJob job) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= job.n_slots * job.n_grid) return;
+  const double* v = reinterpret_cast<const double*>(world + job.off_out) + static_cast<size_t>(row) * job.n_cdf;
+  bool sorted = true;
+  for (uint32_t c = 0; c + 1 < job.n_cdf; c++) sorted = sorted && v[c] <= v[c + 1];
+  if (!sorted || !(v[0] == v[0])) *reinterpret_cast<uint32_t*>(world + job.off_sorted_flag) = 0u;
+}
+
 cudaError_t launch_evaluate_rows(char* world_d, const EvalJob* jobs, size_t n_jobs, cudaStream_t stream) {
   for (size_t k = 0; k < n_jobs; k++) {
     const uint32_t n = jobs[k].n_grid * jobs[k].n_cdf;
     if (n == 0 || jobs[k].n_slots == 0) continue;
     evaluate_rows_kernel<<<dim3((n + 255) / 256, jobs[k].n_slots), 256, 0, stream>>>(world_d, jobs[k]);
+    const uint32_t rows = jobs[k].n_slots * jobs[k].n_grid;
+    check_rows_sorted_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(world_d, jobs[k]);
   }
   return cudaGetLastError();
 }

@@ -142,6 +142,12 @@ struct TslPartition {
   // (cdf, grid, T) and T is a per-cell constant in BASELINE configs[1], [2], [3]: a reconstruction there is ONE load
   // and find_cdf's comparator probes one contiguous row of n_cdf doubles.  0 = none.
   uint32_t off_eval;
+  // 1: every evaluated row is non-decreasing in the CDF node (checked on the device after each evaluation,
+  // kernels.cu check_rows_sorted_kernel).  std::upper_bound over such a row gives the same index whatever the probe
+  // sequence, so find_cdf (ThermalScattering.cpp:398-421) may search it with a few rounds of independent loads instead
+  // of libstdc++'s ~log2(n_cdf) dependent probes.  0: keep libstdc++'s probe sequence (the result of a search over a
+  // row that is not sorted depends on it).
+  uint32_t eval_sorted;
 };
 
 // ThermalScattering
@@ -223,6 +229,7 @@ struct EvalJob {
   uint32_t n_grid, n_cdf, n_T, rank, n_slots;
   uint8_t t_lo[kMaxEvalT], t_hi[kMaxEvalT];  // T_lo_i, T_hi_i of the partition's temperature axis for each T_s
   double dT[kMaxEvalT], tT[kMaxEvalT];       // T_hi - T_lo, T_s - T_lo
+  uint32_t off_sorted_flag;                  // blob offset of the partition's TslPartition::eval_sorted
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.

@@ -118,3 +118,29 @@ def test_evaluated_tables_change_nothing(full_tables, tmp_path, monkeypatch):
             assert np.array_equal(scores, results[0][0]) and np.array_equal(squares, results[0][1])
             assert c == results[0][2]
             assert records == results[0][3]
+
+
+def test_sorted_row_search_changes_nothing(full_tables, monkeypatch):
+    """find_cdf over an evaluated, sorted row as rounds of independent loads (physics_ce.cuh find_cdf_sorted,
+    TslPartition::eval_sorted) against libstdc++'s probe sequence (MMC_TSL_SORTED_SEARCH=0): identical tallies, counters
+    and traces on single_zone and multi_zone at full shape, event-split and fused schedule."""
+    n = 100_000
+    for name in ("single_zone", "multi_zone"):
+        text = FULL_DECKS[name](full_tables, histories=n)
+        results = []
+        for flag in (None, "0"):
+            if flag is None:
+                monkeypatch.delenv("MMC_TSL_SORTED_SEARCH", raising=False)
+            else:
+                monkeypatch.setenv("MMC_TSL_SORTED_SEARCH", flag)
+            for schedule in (capi.SCHEDULE_EVENT, capi.SCHEDULE_FUSED):
+                drv = capi.Driver(text=text)  # the flag is read when the device world is built
+                drv.set_options(schedule=schedule)
+                scores, squares = drv.solve()
+                records = [(int(r.history), int(r.event), int(r.rng_state), float(r.energy), tuple(r.position), tuple(r.direction))
+                           for r in capi.Driver(text=text).trace(0, 40, cap=1 << 16)]
+                results.append((scores, squares, drv.counters(), records))
+        monkeypatch.delenv("MMC_TSL_SORTED_SEARCH", raising=False)
+        for scores, squares, c, records in results[1:]:
+            assert np.array_equal(scores, results[0][0]) and np.array_equal(squares, results[0][1])
+            assert c == results[0][2] and records == results[0][3]
