@@ -941,10 +941,17 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           tt.off_xs_SE = b.add(xs_SE.data(), xs_SE.size());
           tt.off_xs_T = b.add(t.xs_T, t.n_temperature * t.rank);
           std::vector<double> Es, betas;
+          const size_t first_eval_job = eval_jobs.size();
           tt.n_beta_partitions = t.n_beta_partitions;
           tt.off_beta_partitions = partitions(t.beta_partitions, t.n_beta_partitions, Es);
           tt.n_alpha_partitions = t.n_alpha_partitions;
           tt.off_alpha_partitions = partitions(t.alpha_partitions, t.n_alpha_partitions, betas);
+          // every partition evaluated (and, checked on the device, sorted): collisions at an evaluated temperature
+          // sample with ce::tsl_sample_direct
+          const bool sorted_search = !(std::getenv("MMC_TSL_SORTED_SEARCH") && std::atoi(std::getenv("MMC_TSL_SORTED_SEARCH")) == 0);
+          tt.direct = sorted_search && !eval_T.empty() &&
+                              eval_jobs.size() - first_eval_job == static_cast<size_t>(t.n_beta_partitions + t.n_alpha_partitions)
+                          ? 1u : 0u;
           tt.n_Es = static_cast<uint32_t>(Es.size());
           tt.off_Es = b.add(Es.data(), Es.size());
           tt.off_Es_hint = hint(Es.data(), Es.size());
@@ -959,6 +966,8 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           const bool xs_expanded = reserve_dense(t.n_energy * t.n_temperature, xs_tail);
           if (xs_expanded) jobs.push_back(DenseJob{tt.off_xs_SE, tt.off_xs_T, xs_tail, 1u, tt.n_E, tt.n_T, tt.rank, 0u});
           xr.off_tsl = b.add(&tt, 1);
+          for (size_t k = first_eval_job; k < eval_jobs.size(); k++)
+            eval_jobs[k].off_direct_flag = xr.off_tsl + static_cast<uint32_t>(offsetof(TslTable, direct));
           if (xs_expanded) dense_patches.push_back({xr.off_tsl + offsetof(TslTable, off_xs_dense), xs_tail});
         }
       }

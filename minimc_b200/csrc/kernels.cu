@@ -673,7 +673,10 @@ __global__ void check_rows_sorted_kernel(char* world, const __grid_constant__ Ev
   const double* v = reinterpret_cast<const double*>(world + job.off_out) + static_cast<size_t>(row) * job.n_cdf;
   bool sorted = true;
   for (uint32_t c = 0; c + 1 < job.n_cdf; c++) sorted = sorted && v[c] <= v[c + 1];
-  if (!sorted || !(v[0] == v[0])) *reinterpret_cast<uint32_t*>(world + job.off_sorted_flag) = 0u;
+  if (!sorted || !(v[0] == v[0])) {
+    *reinterpret_cast<uint32_t*>(world + job.off_sorted_flag) = 0u;
+    *reinterpret_cast<uint32_t*>(world + job.off_direct_flag) = 0u;
+  }
 }
 
 cudaError_t launch_evaluate_rows(char* world_d, const EvalJob* jobs, size_t n_jobs, cudaStream_t stream) {

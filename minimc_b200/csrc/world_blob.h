@@ -162,8 +162,14 @@ struct TslTable {
   uint32_t off_betas_hint;      // SearchHints of E / Es / betas: off_E_hint, off_Es_hint, off_betas_hint
   uint32_t off_T_hint;          // SearchHint of T
   uint32_t off_xs_dense;        // double[n_E][n_T]: EvaluateInelastic at every (E, T) node, expanded like off_dense; 0 = none
+  // 1: every beta and alpha partition has evaluated tables (off_eval) whose rows are all sorted (eval_sorted): a
+  // collision in a cell with an evaluated temperature samples with ce::tsl_sample_direct.  Set in the image when every
+  // partition got its evaluated table, cleared on the device when a partition's rows turn out unsorted.
+  uint32_t direct;
+  uint32_t pad_direct;
   double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
 };
+
 
 // one ContinuousReaction
 struct CeReaction {
@@ -230,6 +236,7 @@ struct EvalJob {
   uint8_t t_lo[kMaxEvalT], t_hi[kMaxEvalT];  // T_lo_i, T_hi_i of the partition's temperature axis for each T_s
   double dT[kMaxEvalT], tT[kMaxEvalT];       // T_hi - T_lo, T_s - T_lo
   uint32_t off_sorted_flag;                  // blob offset of the partition's TslPartition::eval_sorted
+  uint32_t off_direct_flag;                  // blob offset of its table's TslTable::direct
 };
 
 // One banked particle (secondary or k-eigenvalue site): 64 bytes.

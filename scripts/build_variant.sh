@@ -12,6 +12,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=fa
 nvcc $FLAGS "$@" -c kernels.cu -o build/variants/$NAME.kernels.o &
 nvcc $FLAGS "$@" -Xptxas -v -c event_loop.cu -o build/variants/$NAME.event_loop.o 2>&1 | grep -A2 "event_\(flight\|tsl\)_kernel" | grep -E "Used|spill" || true
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$NAME.so build/variants/$NAME.kernels.o build/variants/$NAME.event_loop.o build/capi.o build/host_*.o
+# (the counter-RNG build of the kernels, the C ABI and the host are the base build's)
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$NAME.so build/variants/$NAME.kernels.o build/variants/$NAME.event_loop.o build/kernels_ctr.o build/event_loop_ctr.o build/capi.o build/comm.o build/host_*.o -ldl
 rm build/variants/$NAME.kernels.o build/variants/$NAME.event_loop.o
 echo built build/variants/$NAME.so
