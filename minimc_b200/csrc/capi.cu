@@ -962,6 +962,23 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
           tt.alpha_cutoff = t.alpha_cutoff;
           tt.awr = t.awr;
           tt.cutoff_energy = t.energy[t.n_energy - 1];  // ThermalScattering.hpp:125-126
+          if (!eval_T.empty()) {
+            // "Find index of Temperature above and below" + r_T of GetTotal at every evaluated temperature
+            // (ThermalScattering.cpp:126-135,152-155; one IEEE subtraction pair and division, -ffp-contract=off)
+            std::vector<TslEvalBracket> brackets(eval_T.size());
+            for (size_t s = 0; s < eval_T.size(); s++) {
+              const double* Ts = t.temperature;
+              const size_t candidate = static_cast<size_t>(std::upper_bound(Ts, Ts + t.n_temperature, eval_T[s]) - Ts);
+              const bool above_max = candidate == t.n_temperature;
+              const size_t hi = above_max ? candidate - 1 : candidate;
+              const bool below_min = hi == 0;
+              const size_t lo = below_min ? hi : hi - 1;
+              brackets[s].lo = static_cast<uint32_t>(lo);
+              brackets[s].hi = static_cast<uint32_t>(hi);
+              brackets[s].r_T = below_min ? 1.0 : above_max ? 0.0 : (eval_T[s] - Ts[lo]) / (Ts[hi] - Ts[lo]);
+            }
+            tt.off_eval_bracket = b.add(brackets.data(), brackets.size());
+          }
           uint32_t xs_tail = 0;
           const bool xs_expanded = reserve_dense(t.n_energy * t.n_temperature, xs_tail);
           if (xs_expanded) jobs.push_back(DenseJob{tt.off_xs_SE, tt.off_xs_T, xs_tail, 1u, tt.n_E, tt.n_T, tt.rank, 0u});
@@ -979,6 +996,18 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
   h.total_bytes = static_cast<uint32_t>(b.bytes.size());
   h.dense_bytes = static_cast<uint32_t>(dense_total);
   h.tsl_all_dense = dense_tables > 0 && dense_complete;
+  // candidates for the direct-only S(a,b) kernel: every material cell at an evaluated temperature, every table direct
+  // (the device still has to confirm that the evaluated rows are sorted: confirm_direct)
+  {
+    bool all = G == 0 && !eval_jobs.empty();
+    for (int c = 0; c < d->n_cells && all; c++) all = d->cell_material[c] < 0 || cell_eval_slot[c] >= 0;
+    for (const EvalJob& job : eval_jobs) {
+      uint32_t flag = 0;
+      std::memcpy(&flag, b.bytes.data() + job.off_direct_flag, sizeof(flag));
+      all = all && flag == 1u;
+    }
+    h.tsl_all_direct = all ? 1u : 0u;
+  }
   for (const DensePatch& patch : dense_patches) {
     const uint32_t absolute = h.total_bytes + patch.tail_offset;
     std::memcpy(b.bytes.data() + patch.field_at, &absolute, sizeof(uint32_t));
@@ -989,6 +1018,22 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
   header_out = h;
   has_fission_out = has_fission;
   return MMC_OK;
+}
+
+// After the evaluated rows were checked on the device (check_rows_sorted_kernel clears TslTable::direct of a table with
+// an unsorted row): the host's copy of the header keeps tsl_all_direct only if every table is still direct.
+cudaError_t confirm_direct(const char* d_blob, const std::vector<EvalJob>& eval_jobs, WorldHeader& h) {
+  if (!h.tsl_all_direct) return cudaSuccess;
+  uint32_t last = 0;
+  for (const EvalJob& job : eval_jobs) {
+    if (job.off_direct_flag == last) continue;
+    last = job.off_direct_flag;
+    uint32_t flag = 0;
+    const cudaError_t e = cudaMemcpy(&flag, d_blob + job.off_direct_flag, sizeof(flag), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    if (flag != 1u) h.tsl_all_direct = 0;
+  }
+  return cudaSuccess;
 }
 }  // namespace
 
@@ -1023,6 +1068,7 @@ int mmc_world_create(const mmc_world_desc* d, int device, mmc_world** out) {
   if (e == cudaSuccess) e = launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream);
   if (e == cudaSuccess) e = launch_evaluate_rows(w->d_blob, eval_jobs.data(), eval_jobs.size(), w->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+  if (e == cudaSuccess) e = confirm_direct(w->d_blob, eval_jobs, w->header);
   if (e != cudaSuccess) {
     mmc_world_destroy(w);
     return fail(MMC_ERR_CUDA, "mmc_world_create: %s", cudaGetErrorString(e));
@@ -1052,6 +1098,7 @@ int mmc_world_update(mmc_world* w, const mmc_world_desc* d) {
   MMC_CUDA(launch_expand_dense(w->d_blob, dense_jobs.data(), dense_jobs.size(), w->stream));
   MMC_CUDA(launch_evaluate_rows(w->d_blob, eval_jobs.data(), eval_jobs.size(), w->stream));
   MMC_CUDA(cudaStreamSynchronize(w->stream));
+  MMC_CUDA(confirm_direct(w->d_blob, eval_jobs, h));
   w->header = h;
   return MMC_OK;
 }

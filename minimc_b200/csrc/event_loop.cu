@@ -29,7 +29,7 @@
 
 // flight kernel CTA: threads, and resident CTAs per SM the register allocation is tuned for (768 threads per SM)
 #ifndef MMC_EV_FLIGHT_THREADS
-#define MMC_EV_FLIGHT_THREADS 256
+#define MMC_EV_FLIGHT_THREADS 128
 #endif
 #ifndef MMC_EV_FLIGHT_BLOCKS
 #define MMC_EV_FLIGHT_BLOCKS (768 / MMC_EV_FLIGHT_THREADS)
@@ -51,6 +51,11 @@
 // registers, so more, thinner threads to cover the L2 latency of the table gathers
 #ifndef MMC_EV_TSL_DENSE_THREADS
 #define MMC_EV_TSL_DENSE_THREADS 768
+#endif
+// the S(a,b) kernel of worlds whose every collision samples over evaluated rows (WorldHeader::tsl_all_direct): nothing
+// but ce::tsl_sample_direct -- no sampler state machine, no spills
+#ifndef MMC_EV_TSL_DIRECT_THREADS
+#define MMC_EV_TSL_DIRECT_THREADS 1024
 #endif
 #ifndef MMC_STATE_CACHE_GLOBAL
 #define MMC_STATE_CACHE_GLOBAL 1
@@ -94,8 +99,12 @@ constexpr int kFlightThreads = MMC_EV_FLIGHT_THREADS;
 constexpr int kWarpsPerBlock = kFlightThreads / 32;
 constexpr int kTslThreads = MMC_EV_TSL_THREADS;
 constexpr int kTslDenseThreads = MMC_EV_TSL_DENSE_THREADS;
+constexpr int kTslDirectThreads = MMC_EV_TSL_DIRECT_THREADS;
 // kinds of the S(a,b) kernel: where a reconstruction reads from
-enum : int { kTslRowsGlobalSc = 0, kTslRowsSharedSc = 1, kTslDense = 2 };
+enum : int { kTslRowsGlobalSc = 0, kTslRowsSharedSc = 1, kTslDense = 2, kTslDirect = 3 };
+__host__ __device__ constexpr int tsl_threads_of(int kind) {
+  return kind == kTslDirect ? kTslDirectThreads : kind == kTslDense ? kTslDenseThreads : kTslThreads;
+}
 constexpr size_t kTslRowBytes = MMC_EV_TSL_ROWS_IN_REGS ? 0 : 10 * kTslThreads * sizeof(double2);
 
 // exclusive prefix of this warp among the CTA's warp totals, and the CTA total
@@ -145,9 +154,10 @@ struct CtaCompactor {
   uint32_t base[kQueues];
 };
 
-template <int kQueues>
+template <int kQueues, typename BeforeBarrier, typename AfterBarrier>
 __device__ __forceinline__ void cta_compact(
-    CtaCompactor<kQueues>& sm, const bool (&flag)[kQueues], unsigned int* const (&counter)[kQueues], uint32_t (&position)[kQueues]) {
+    CtaCompactor<kQueues>& sm, const bool (&flag)[kQueues], unsigned int* const (&counter)[kQueues], uint32_t (&position)[kQueues],
+    BeforeBarrier before_barrier, AfterBarrier after_barrier) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
   unsigned mask[kQueues];
@@ -156,7 +166,9 @@ __device__ __forceinline__ void cta_compact(
     mask[k] = __ballot_sync(kFull, flag[k]);
     if (lane == 0) sm.totals[k][warp] = __popc(mask[k]);
   }
+  before_barrier();
   __syncthreads();
+  after_barrier();
   if (threadIdx.x < kQueues) {
     uint32_t total = 0;
     for (int wi = 0; wi < kWarpsPerBlock; wi++) total += sm.totals[threadIdx.x][wi];
@@ -171,9 +183,9 @@ __device__ __forceinline__ void cta_compact(
 }
 
 // per-CTA counter flush: the 0/1-per-lane counters packed four to a word, one warp reduction (REDUX) per word, the
-// warp sums through shared memory, one atomic per non-zero counter and CTA into one of 64 replicas
-__device__ __forceinline__ void flush_counters_cta(
-    const ThreadCounters& c, bool has_secondaries, uint4* s_packed, unsigned long long* counter_replicas) {
+// warp sums through shared memory, one atomic per non-zero counter and CTA into one of 64 replicas.  In two halves
+// around a CTA barrier the caller has anyway (the flight kernel's is the first barrier of its stream compaction).
+__device__ __forceinline__ void stage_counters_cta(const ThreadCounters& c, bool has_secondaries, uint4* s_packed) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t pa = c.events | (c.collisions << 8) | (c.crossings << 16) | (c.virtuals << 24);
   const uint32_t pb = c.histories | (c.births << 8) | (c.lost << 16) | (c.physics << 24);
@@ -181,11 +193,13 @@ __device__ __forceinline__ void flush_counters_cta(
   const uint32_t sa = __reduce_add_sync(kFull, pa), sb = __reduce_add_sync(kFull, pb), sd = __reduce_add_sync(kFull, pd);
   const uint32_t ss = has_secondaries ? __reduce_add_sync(kFull, c.secondaries) : 0u;
   if (lane == 0) s_packed[warp] = make_uint4(sa, sb, sd, ss);
-  __syncthreads();
-  if (threadIdx.x < kNumCounters) {
+}
+// after the barrier: threads first_thread .. first_thread + kNumCounters - 1 add one counter each
+__device__ __forceinline__ void commit_counters_cta(const uint4* s_packed, uint32_t first_thread, unsigned long long* counter_replicas) {
+  if (threadIdx.x >= first_thread && threadIdx.x < first_thread + kNumCounters) {
     // mmc_counters order: histories, births, events, collisions, crossings, virtual, scores, secondaries, banked,
     // lost, capacity, physics -> (word, shift, mask) of the packed sums
-    const uint32_t k = threadIdx.x;
+    const uint32_t k = threadIdx.x - first_thread;
     const uint32_t word = (k == 2 || k == 3 || k == 4 || k == 5) ? 0u : (k == 0 || k == 1 || k == 9 || k == 11) ? 1u : (k == 6 || k == 10) ? 2u : 3u;
     const uint32_t shift = k == 3 ? 8u : k == 4 ? 16u : k == 5 ? 24u : k == 1 ? 8u : k == 9 ? 16u : k == 11 ? 24u : k == 10 ? 16u : 0u;
     const uint32_t mask = word < 2u ? 0xffu : word == 2u ? 0xffffu : 0xffffffffu;
@@ -277,11 +291,13 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
   const bool flag[3] = {!retired, alive && o.need_tsl, !retired && (o.need_cross || !is_alive(p.event))};
   unsigned int* const counter[3] = {&q.count[parity ^ 1u], &q.count[2u + parity], &q.count[5u + parity]};
   uint32_t position[3];
-  cta_compact<3>(s_compact, flag, counter, position);
+  // the counters ride on the compaction's first barrier: staged before it, added (by the second warp) after it
+  cta_compact<3>(s_compact, flag, counter, position,
+                 [&]() { stage_counters_cta(c, has_secondaries, s_packed); },
+                 [&]() { commit_counters_cta(s_packed, kFlightThreads >= 64 ? 32u : 0u, counter_replicas); });
   if (flag[0]) q.alive[parity ^ 1u][position[0]] = slot;
   if (flag[1]) q.tsl[position[1]] = slot;
   if (flag[2]) q.boundary[position[2]] = slot;
-  flush_counters_cta(c, has_secondaries, s_packed, counter_replicas);
 }
 
 // ---- boundary: the rare ends of an event, run densely over the slots the flight kernel queued.
@@ -479,12 +495,12 @@ __global__ void __launch_bounds__(kFlightThreads) event_boundary_kernel(
 //       rows that differ modulo 8 never conflict).
 // Warps claim chunks of 32 queue entries from a counter; state loads and stores are coalesced over the compacted queue.
 template <int kKind>
-__global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslThreads, 1) event_tsl_kernel(
+__global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
     const char* __restrict__ world_g, const __grid_constant__ WorldHeader header, const __grid_constant__ RunSpec run,
     const __grid_constant__ EventState st, const __grid_constant__ EventQueues q, uint32_t pass,
     const __grid_constant__ BoundaryArgs args, unsigned long long* counter_replicas) {
   constexpr bool kSharedSc = kKind == kTslRowsSharedSc;
-  constexpr uint32_t kThreads = kKind == kTslDense ? kTslDenseThreads : kTslThreads;
+  constexpr uint32_t kThreads = tsl_threads_of(kKind);
   extern __shared__ __align__(16) char smem[];
   [[maybe_unused]] double2* s_rows = reinterpret_cast<double2*>(smem);  // SharedRows: double2[10][kTslThreads]
   [[maybe_unused]] char* s_sc = smem + kTslRowBytes;
@@ -523,14 +539,14 @@ __global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslTh
   }
 #endif
   auto make_rows = [&]() {
-    if constexpr (kKind == kTslDense) return ce::DenseRows{};
+    if constexpr (kKind == kTslDense || kKind == kTslDirect) return ce::DenseRows{};
 #if MMC_EV_TSL_ROWS_IN_REGS
     else return ce::RegisterRows<kSharedSc>(s_sc, w.h->off_sc_arena);
 #else
     else return ce::SharedRows<kTslThreads, kSharedSc>(s_rows, s_sc, w.h->off_sc_arena);
 #endif
   };
-  auto rows = make_rows();
+  [[maybe_unused]] auto rows = make_rows();
   // warps claim chunks of 32 queue entries from one counter: a scatter takes 10-30 rounds of reconstructions, so a
   // static split leaves the unlucky warps running alone at the end of every pass (chunks of 64: no faster)
   // Guided self-scheduling: a claim takes 1/(2 x warps) of what is left, between 32 and 256 entries -- a quarter of the
@@ -565,7 +581,14 @@ __global__ void __launch_bounds__(kKind == kTslDense ? kTslDenseThreads : kTslTh
     const TslTable& t = *w.at<TslTable>(MMC_LD(st.tsl_off[slot]));
     bool error = false;
     double mu = 0, E_p = 0;
-    ce::tsl_sample(w, t, p.rng, p.energy, T, ce::cell_eval_slot(w, MMC_LD(st.cell[slot])), error, rows, mu, E_p);
+    const int32_t eval_slot = ce::cell_eval_slot(w, MMC_LD(st.cell[slot]));
+    if constexpr (kKind == kTslDirect) {
+      // WorldHeader::tsl_all_direct promises both; a collision that breaks the promise is reported, not sampled
+      if (eval_slot >= 0 && t.direct) ce::tsl_sample_direct(w, t, p.rng, p.energy, T, eval_slot, error, mu, E_p);
+      else error = true;
+    } else {
+      ce::tsl_sample(w, t, p.rng, p.energy, T, eval_slot, error, rows, mu, E_p);
+    }
     if (!error) {
       // the direction is only needed now: it stays in memory while the sampler's state fills the registers
       p.dx = MMC_LD(st.dx[slot]), p.dy = MMC_LD(st.dy[slot]), p.dz = MMC_LD(st.dz[slot]);
@@ -631,10 +654,12 @@ cudaError_t launch_event_pass(
 #endif
   if (marks) cudaEventRecord(marks[1], stream);
   // S(a,b) kernel: persistent, at most one CTA per SM, no more CTAs than the queues can feed
-  const uint32_t per_cta = header.tsl_all_dense ? kTslDenseThreads : kTslThreads;
+  const uint32_t per_cta = header.tsl_all_direct ? kTslDirectThreads : header.tsl_all_dense ? kTslDenseThreads : kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
   if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
-  if (header.tsl_all_dense)
+  if (header.tsl_all_direct)
+    event_tsl_kernel<kTslDirect><<<tsl_blocks, kTslDirectThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+  else if (header.tsl_all_dense)
     event_tsl_kernel<kTslDense><<<tsl_blocks, kTslDenseThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
   else if (tsl.shared_sc)
     event_tsl_kernel<kTslRowsSharedSc><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(

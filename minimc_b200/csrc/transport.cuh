@@ -616,7 +616,7 @@ __device__ __forceinline__ void transport_step(
       majorant = ce::material_majorant(w, mat, p.energy, T, ce::cell_temperature_upper(w, p.cell), error);
       micro = 0;  // evaluated below, only when a collision is a candidate
     } else {
-      micro = majorant = ce::material_total(w, mat, p.energy, T, error, &ev);
+      micro = majorant = ce::material_total(w, mat, p.energy, T, error, &ev, ce::cell_eval_slot(w, p.cell));
     }
     if (error) {
       out.error_physics = true;
@@ -650,7 +650,8 @@ __device__ __forceinline__ void transport_step(
       // bernoulli_distribution{total / majorant}: u < p, both evaluated BEFORE the particle streams
       if (kCE) {
         bool error = false;
-        micro = ce::material_total(w, mat, p.energy, ce::cell_temperature(w, p.cell, p.px, p.py, p.pz), error, &ev);
+        micro = ce::material_total(w, mat, p.energy, ce::cell_temperature(w, p.cell, p.px, p.py, p.pz), error, &ev,
+                                   ce::cell_eval_slot(w, p.cell));
         if (error) {
           out.error_physics = true;
           p.event = MMC_EV_CAPTURE;

@@ -92,7 +92,11 @@ struct WorldHeader {
   // (TslPartition::off_eval), -1 for void cells, cells with a linear temperature field and cells past kMaxEvalT
   uint32_t off_cell_eval_slot;
   int32_t n_eval_T;
-  uint32_t pad1;
+  // 1 when every collision the S(a,b) kernel can be handed samples with ce::tsl_sample_direct: every material cell has
+  // an evaluated temperature (off_cell_eval_slot >= 0) and every table is TslTable::direct -- the host's copy of the
+  // header is corrected after the device has checked the rows (capi.cu confirm_direct); selects the S(a,b) kernel kind
+  // that holds nothing but that sampler
+  uint32_t tsl_all_direct;
 };
 
 // distinct constant cell temperatures a world keeps evaluated S(a,b) tables for (BASELINE configs: 1, 13, 1, 0)
@@ -150,6 +154,12 @@ struct TslPartition {
   uint32_t eval_sorted;
 };
 
+// GetTotal's temperature bracket at one evaluated temperature
+struct TslEvalBracket {
+  uint32_t lo, hi;  // T_lo_i, T_hi_i
+  double r_T;       // below_T_min ? 1 : above_T_max ? 0 : (T - T_lo) / (T_hi - T_lo)
+};
+
 // ThermalScattering
 struct TslTable {
   Table1D majorant;
@@ -166,7 +176,9 @@ struct TslTable {
   // collision in a cell with an evaluated temperature samples with ce::tsl_sample_direct.  Set in the image when every
   // partition got its evaluated table, cleared on the device when a partition's rows turn out unsorted.
   uint32_t direct;
-  uint32_t pad_direct;
+  // TslEvalBracket[WorldHeader::n_eval_T]: the temperature bracket of GetTotal (ThermalScattering.cpp:126-135,152-155)
+  // at each evaluated cell temperature -- T_lo_i, T_hi_i and r_T are functions of T alone; 0 = none
+  uint32_t off_eval_bracket;
   double beta_cutoff, alpha_cutoff, awr, cutoff_energy;
 };
 
