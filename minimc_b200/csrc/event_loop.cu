@@ -269,8 +269,12 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
     transport_step<kTracking, true, false, true, false, true>(w, p, dq, o);
     count_event(c, p, o);
     MMC_ST(st.px[slot], p.px), MMC_ST(st.py[slot], p.py), MMC_ST(st.pz[slot], p.pz);
-    MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
-    MMC_ST(st.energy[slot], p.energy);
+    // direction and energy change in this kernel only where a scatter is sampled here (free gas): a flight to a
+    // surface, a virtual collision and a collision whose S(a,b) sampling is still to come leave both as loaded
+    if (p.event == MMC_EV_SCATTER && !o.need_tsl) {
+      MMC_ST(st.dx[slot], p.dx), MMC_ST(st.dy[slot], p.dy), MMC_ST(st.dz[slot], p.dz);
+      MMC_ST(st.energy[slot], p.energy);
+    }
     store_rng<false>(st, slot, p.rng);
     MMC_ST(st.event[slot], p.event);
     if (o.need_cross) MMC_ST(st.surface[slot], p.surface);
@@ -279,7 +283,8 @@ __global__ void __launch_bounds__(kFlightThreads, MMC_EV_FLIGHT_BLOCKS) event_fl
       MMC_ST(st.dq_count[slot], dq.count);
     }
     if (o.need_tsl) {
-      MMC_ST(st.tsl_T[slot], o.tsl_T);
+      // (the direct S(a,b) kernel reads the temperature of an evaluated cell from the cell's field record)
+      if (!header.tsl_all_direct) MMC_ST(st.tsl_T[slot], o.tsl_T);
       MMC_ST(st.tsl_off[slot], o.tsl_off);
     }
   }
@@ -577,11 +582,13 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
     Particle p;
     p.energy = MMC_LD(st.energy[slot]);
     p.rng = load_rng(st, slot);
-    const double T = MMC_LD(st.tsl_T[slot]);
+    const int32_t cell = MMC_LD(st.cell[slot]);
+    // ScalarField::at of a constant field is its value (ce::cell_temperature): the flight kernel does not pass it on
+    const double T = kKind == kTslDirect ? __ldg(w.at<double>(w.h->off_cell_field_param) + 6 * cell) : MMC_LD(st.tsl_T[slot]);
     const TslTable& t = *w.at<TslTable>(MMC_LD(st.tsl_off[slot]));
     bool error = false;
     double mu = 0, E_p = 0;
-    const int32_t eval_slot = ce::cell_eval_slot(w, MMC_LD(st.cell[slot]));
+    const int32_t eval_slot = ce::cell_eval_slot(w, cell);
     if constexpr (kKind == kTslDirect) {
       // WorldHeader::tsl_all_direct promises both; a collision that breaks the promise is reported, not sampled
       if (eval_slot >= 0 && t.direct) ce::tsl_sample_direct(w, t, p.rng, p.energy, T, eval_slot, error, mu, E_p);

@@ -26,10 +26,12 @@ launches) echo "== ncu launch list"
     python bench.py --steps 1 --warmup 1 --histories-per-gpu 4194304 --no-cpu-baseline --no-multigroup > $OUT/bench_under_ncu.log 2>&1;;
 ncu_tsl) echo "== ncu full: S(a,b) kernel of a steady-state pass"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_tsl -s ${NCU_SKIP:-6} -c 1 -o $OUT/prof_tsl \
-    python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_tsl.log 2>&1;;
+    python bench.py --steps 1 --warmup 0 --histories-per-gpu ${NCU_HIST:-16777216} --no-cpu-baseline --no-multigroup --no-extras > $OUT/ncu_tsl.log 2>&1;;
 ncu_flight) echo "== ncu full: flight kernel of a steady-state pass"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_flight_kernel -s ${NCU_SKIP:-6} -c 1 -o $OUT/prof_flight \
-    python bench.py --steps 1 --warmup 0 --histories-per-gpu 8388608 --no-cpu-baseline --no-multigroup > $OUT/ncu_flight.log 2>&1;;
+    python bench.py --steps 1 --warmup 0 --histories-per-gpu ${NCU_HIST:-16777216} --no-cpu-baseline --no-multigroup --no-extras > $OUT/ncu_flight.log 2>&1;;
+slots) for n in 1048576 4194304; do
+  echo "== bench single_zone with $n slots"; MMC_EVENT_SLOTS=$n timeout 900 python bench.py --steps 5 --warmup 3 --no-multigroup --no-cpu-baseline --no-extras 2>$OUT/bench_slots$n.err | tee $OUT/bench_slots$n.json; done;;
 *) echo "unknown stage $st";;
 esac; done
 ls -la $OUT
