@@ -801,9 +801,12 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
         cum[k + 1]++;
       }
       for (uint32_t k = 0; k < sh.n_buckets; k++) cum[k + 1] += cum[k];
-      std::vector<char> image(sizeof(SearchHint) + cum.size() * sizeof(uint32_t));
+      // stored as pairs {cum[k], cum[k + 1]}: a bucket's range is one 8-byte load
+      std::vector<uint32_t> pairs(2 * static_cast<size_t>(sh.n_buckets));
+      for (uint32_t k = 0; k < sh.n_buckets; k++) pairs[2 * k] = cum[k], pairs[2 * k + 1] = cum[k + 1];
+      std::vector<char> image(sizeof(SearchHint) + pairs.size() * sizeof(uint32_t));
       std::memcpy(image.data(), &sh, sizeof(SearchHint));
-      std::memcpy(image.data() + sizeof(SearchHint), cum.data(), cum.size() * sizeof(uint32_t));
+      std::memcpy(image.data() + sizeof(SearchHint), pairs.data(), pairs.size() * sizeof(uint32_t));
       return b.add(image.data(), image.size());
     };
     auto table = [&b, &hint](const mmc_table1d& t) {
@@ -856,6 +859,14 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
         o.rank = static_cast<uint32_t>(q.rank);
         o.off_cdf = b.add(q.cdf, q.n_cdf);
         o.off_cdf_hint = hint(q.cdf, q.n_cdf);
+        {
+          std::vector<double> pairs(2 * (q.n_cdf + 1));
+          for (uint64_t c = 0; c <= q.n_cdf; c++) {
+            pairs[2 * c] = c != 0 ? q.cdf[c - 1] : 0.0;
+            pairs[2 * c + 1] = c != q.n_cdf ? q.cdf[c] : 1.0;
+          }
+          o.off_cdf_pairs = b.add(pairs.data(), pairs.size());
+        }
         o.off_T = b.add(q.temperature, q.n_temperature);
         o.off_T_hint = hint(q.temperature, q.n_temperature);
         o.off_scaled_cdf_modes = sc_offsets[sc_next++];  // in the arena, same traversal order

@@ -119,8 +119,8 @@ struct Table1D {
 struct SearchHint {
   int64_t first_bucket;  // bucket number (bits >> shift) of the first positive element, minus 1
   uint32_t shift;
-  uint32_t n_buckets;    // cum has n_buckets + 1 entries; bucket 0 = everything below the first positive element
-  // uint32_t cum[n_buckets + 1] follows
+  uint32_t n_buckets;    // bucket 0 = everything below the first positive element
+  // uint2 range[n_buckets] follows: {cum[k], cum[k + 1]}, one 8-byte load per search (the header is one 16-byte load)
 };
 
 // ThermalScattering::BetaPartition / AlphaPartition
@@ -152,6 +152,10 @@ struct TslPartition {
   // of libstdc++'s ~log2(n_cdf) dependent probes.  0: keep libstdc++'s probe sequence (the result of a search over a
   // row that is not sorted depends on it).
   uint32_t eval_sorted;
+  // double2[n_cdf + 1]: {F_lo, F_hi} of the CDF bracket whose upper index is i -- {cdf[i - 1] or 0, cdf[i] or 1}, the
+  // pair ThermalScattering.cpp:313-320,438-447 reads after every search, as one 16-byte load
+  uint32_t off_cdf_pairs;
+  uint32_t pad_partition;
 };
 
 // GetTotal's temperature bracket at one evaluated temperature
