@@ -866,6 +866,16 @@ int build_world_blob(const mmc_world_desc* d, BlobBuilder& b, WorldHeader& heade
             pairs[2 * c + 1] = c != q.n_cdf ? q.cdf[c] : 1.0;
           }
           o.off_cdf_pairs = b.add(pairs.data(), pairs.size());
+          bool usable = q.n_cdf <= 255;
+          for (uint64_t c = 0; c < q.n_cdf && usable; c++)
+            usable = q.cdf[c] >= 0.0 && q.cdf[c] <= 1.0 && (c == 0 || q.cdf[c - 1] <= q.cdf[c]);
+          o.off_cdf_lut = 0;
+          if (usable) {
+            std::vector<uint8_t> lut(kCdfLut);
+            for (uint32_t k = 0; k < kCdfLut; k++)
+              lut[k] = static_cast<uint8_t>(std::upper_bound(q.cdf, q.cdf + q.n_cdf, static_cast<double>(k) / kCdfLut) - q.cdf);
+            o.off_cdf_lut = b.add(lut.data(), lut.size());
+          }
         }
         o.off_T = b.add(q.temperature, q.n_temperature);
         o.off_T_hint = hint(q.temperature, q.n_temperature);

@@ -591,8 +591,12 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
     const int32_t eval_slot = ce::cell_eval_slot(w, cell);
     if constexpr (kKind == kTslDirect) {
       // WorldHeader::tsl_all_direct promises both; a collision that breaks the promise is reported, not sampled
-      if (eval_slot >= 0 && t.direct) ce::tsl_sample_direct(w, t, p.rng, p.energy, T, eval_slot, error, mu, E_p);
+      if (eval_slot >= 0 && t.direct) ce::tsl_sample_direct<true>(w, t, p.rng, p.energy, T, eval_slot, error, mu, E_p);
       else error = true;
+    } else if constexpr (kKind == kTslDense) {
+      // every partition has its dense table (WorldHeader::tsl_all_dense): a row is evaluated (one load per node) or
+      // two rows of the dense table + the interpolation in T -- the samplers written straight down for both
+      ce::tsl_sample_direct<false>(w, t, p.rng, p.energy, T, eval_slot, error, mu, E_p);
     } else {
       ce::tsl_sample(w, t, p.rng, p.energy, T, eval_slot, error, rows, mu, E_p);
     }

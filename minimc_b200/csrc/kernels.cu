@@ -70,8 +70,12 @@ __device__ __forceinline__ const char* stage_world(const char* world_g, uint32_t
 // indirect effect x estimator score into the sensitivity's per-history pending table (ScorableProxy::Score,
 // Scorable.cpp:81-99), committed -- sum and sum squared -- when the history ends (CommitHistory, :101-106).  These
 // tallies are real-valued: fp64 atomics, order-dependent in the last bits exactly as the reference's own worker merge.
-template <int kTracking, bool kCE, bool kGeneration, bool kPerturb>
-__global__ void __launch_bounds__(kThreadsPerBlock, kCE ? MMC_CE_BLOCKS_PER_SM : MMC_MG_BLOCKS_PER_SM) fixed_source_kernel(
+//
+// kDrain = true: the instantiation the event-split schedule hands its last few thousand histories to (ResumeIO).  Few
+// warps, each alone on its scheduler: the time of that kernel is the longest remaining history times the latency of
+// one event, so it is compiled for one CTA per SM -- all the registers it wants, no spills -- instead of three.
+template <int kTracking, bool kCE, bool kGeneration, bool kPerturb, bool kDrain = false>
+__global__ void __launch_bounds__(kThreadsPerBlock, kDrain ? 1 : kCE ? MMC_CE_BLOCKS_PER_SM : MMC_MG_BLOCKS_PER_SM) fixed_source_kernel(
     const char* __restrict__ world_g, const __grid_constant__ RunSpec run, const double* __restrict__ bounds,
     BankSite* __restrict__ site_scratch, uint2* __restrict__ pending_scratch, unsigned long long* next_history,
     unsigned long long* scores, unsigned long long* square_scores, mmc_counters* counters,
@@ -784,6 +788,13 @@ cudaError_t launch_fixed_source(
   const GenerationIO io = generation ? *generation : GenerationIO{};
   const ResumeIO rs = resume ? *resume : ResumeIO{};
   const SensitivityIO se = sensitivity ? *sensitivity : SensitivityIO{};
+  if (resume && run.continuous_energy && !generation && !sensitivity) {  // the drain of an event-split run
+    auto drain = run.tracking == MMC_TRACK_CELL_DELTA ? fixed_source_kernel<MMC_TRACK_CELL_DELTA, true, false, false, true>
+                                                      : fixed_source_kernel<MMC_TRACK_SURFACE, true, false, false, true>;
+    drain<<<cfg.blocks, kThreadsPerBlock, smem, stream>>>(
+        world_d, run, bounds_d, site_scratch, pending_scratch, next_history, scores, square_scores, counters, io, rs, se);
+    return cudaGetLastError();
+  }
   return dispatch_history_kernel(run.tracking, run.continuous_energy != 0, generation != nullptr, sensitivity != nullptr, [&](auto kernel) -> cudaError_t {
     if (smem > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

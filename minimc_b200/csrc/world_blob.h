@@ -155,8 +155,12 @@ struct TslPartition {
   // double2[n_cdf + 1]: {F_lo, F_hi} of the CDF bracket whose upper index is i -- {cdf[i - 1] or 0, cdf[i] or 1}, the
   // pair ThermalScattering.cpp:313-320,438-447 reads after every search, as one 16-byte load
   uint32_t off_cdf_pairs;
-  uint32_t pad_partition;
+  // uint8[kCdfLut]: lut[k] = std::upper_bound(cdf, k / kCdfLut) -- the sampled CDF value F is uniform, so bucket
+  // floor(F * kCdfLut) almost always names the bracket outright: one byte load, then the pair above confirms it (or the
+  // index moves up a node).  0 = none (more than 255 nodes, or an axis that is not sorted inside [0, 1]).
+  uint32_t off_cdf_lut;
 };
+constexpr uint32_t kCdfLut = 1024;
 
 // GetTotal's temperature bracket at one evaluated temperature
 struct TslEvalBracket {
