@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
     q.count[5u + (parity ^ 1u)] = 0; // the boundary queue of the next pass
   }
   const uint32_t n = q.count[2u + parity];
-  constexpr uint32_t kWarps = kThreads / 32;
+  [[maybe_unused]] constexpr uint32_t kWarps = kThreads / 32;
 #if !MMC_EV_MERGE_BOUNDARY
   if (blockIdx.x * kWarps * 32u >= n) return;  // CTA-uniform: not even the first warp has work
 #endif
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
   {
     // the boundary queue first: chunks of 32 entries claimed from a counter (zeroed by the flight kernel)
     const uint32_t n_boundary = q.count[5u + parity];
-    unsigned long long* replica = counter_replicas + ((blockIdx.x * kWarps + (threadIdx.x >> 5)) % kCounterReplicas) * kNumCounters;
+    unsigned long long* replica = counter_replicas + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % kCounterReplicas) * kNumCounters;
     while (true) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&q.count[7], 32u);
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
   // Guided self-scheduling: a claim takes 1/(2 x warps) of what is left, between 32 and 256 entries -- a quarter of the
   // same-address atomics of fixed 32-entry chunks (ncu r02a: 11 % of this kernel's stall samples sat on that atomic),
   // and still single chunks at the end of the pass, where balance matters.
-  const uint32_t total_warps = gridDim.x * kWarps;
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);  // (a thin CTA when few slots are alive: launch_event_pass)
   uint32_t claim_next = 0, claim_end = 0;
   while (true) {
     if (claim_next >= claim_end) {
@@ -668,10 +668,19 @@ cudaError_t launch_event_pass(
   const uint32_t per_cta = header.tsl_all_direct ? kTslDirectThreads : header.tsl_all_dense ? kTslDenseThreads : kTslThreads;
   uint32_t tsl_blocks = (alive_upper_bound + per_cta - 1) / per_cta;
   if (tsl_blocks > tsl.sm_count) tsl_blocks = tsl.sm_count;
+  // Few slots alive (the ramp-down of a batch): a pass costs the latency of one chunk, and that is lowest when the
+  // chunks are spread over every SM -- one CTA per SM with as few warps as the work needs -- instead of filling a few
+  // SMs with 32 warps each.  (Only the kinds without per-CTA shared-memory rows.)
+  uint32_t thin_threads = 0;
+  if ((header.tsl_all_direct || header.tsl_all_dense) && alive_upper_bound < per_cta * tsl.sm_count) {
+    thin_threads = ((alive_upper_bound + tsl.sm_count - 1) / tsl.sm_count + 31u) & ~31u;
+    if (thin_threads < 64u) thin_threads = 64u;
+    tsl_blocks = tsl.sm_count;
+  }
   if (header.tsl_all_direct)
-    event_tsl_kernel<kTslDirect><<<tsl_blocks, kTslDirectThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+    event_tsl_kernel<kTslDirect><<<tsl_blocks, thin_threads ? thin_threads : kTslDirectThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
   else if (header.tsl_all_dense)
-    event_tsl_kernel<kTslDense><<<tsl_blocks, kTslDenseThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
+    event_tsl_kernel<kTslDense><<<tsl_blocks, thin_threads ? thin_threads : kTslDenseThreads, 0, stream>>>(world_d, header, run, st, q, pass, args, counter_replicas);
   else if (tsl.shared_sc)
     event_tsl_kernel<kTslRowsSharedSc><<<tsl_blocks, kTslThreads, kTslRowBytes + tsl.sc_arena_bytes, stream>>>(
         world_d, header, run, st, q, pass, args, counter_replicas);
