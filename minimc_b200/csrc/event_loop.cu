@@ -57,6 +57,10 @@
 #ifndef MMC_EV_TSL_DIRECT_THREADS
 #define MMC_EV_TSL_DIRECT_THREADS 1024
 #endif
+// share of a pass's S(a,b) queue that the warps of the persistent kernel take as fixed contiguous pieces (no atomics)
+#ifndef MMC_EV_TSL_STATIC_PCT
+#define MMC_EV_TSL_STATIC_PCT 75
+#endif
 #ifndef MMC_STATE_CACHE_GLOBAL
 #define MMC_STATE_CACHE_GLOBAL 1
 #endif
@@ -557,17 +561,22 @@ __global__ void __launch_bounds__(tsl_threads_of(kKind), 1) event_tsl_kernel(
   // Guided self-scheduling: a claim takes 1/(2 x warps) of what is left, between 32 and 256 entries -- a quarter of the
   // same-address atomics of fixed 32-entry chunks (ncu r02a: 11 % of this kernel's stall samples sat on that atomic),
   // and still single chunks at the end of the pass, where balance matters.
+  // The first MMC_EV_TSL_STATIC_PCT per cent of the queue are dealt out without any atomic -- warp k takes entries
+  // [k * share, (k + 1) * share) -- and only the rest is claimed dynamically: that rest evens out what the static
+  // shares leave uneven (a share is ~10 chunks, the spread of their sum a few per cent), with a fraction of the claims.
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);  // (a thin CTA when few slots are alive: launch_event_pass)
-  uint32_t claim_next = 0, claim_end = 0;
+  const uint32_t share = static_cast<uint32_t>((static_cast<uint64_t>(n) * MMC_EV_TSL_STATIC_PCT / 100u) / total_warps) & ~31u;
+  const uint32_t static_total = share * total_warps;
+  uint32_t claim_next = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * share, claim_end = claim_next + share;
   while (true) {
     if (claim_next >= claim_end) {
       uint32_t base = 0, size = 0;
       if (lane == 0) {
-        const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(&q.count[4]);
+        const uint32_t seen = static_total + *reinterpret_cast<volatile unsigned int*>(&q.count[4]);
         const uint32_t left = seen < n ? n - seen : 0u;
         size = left / (2u * total_warps);
         size = size > 256u ? 256u : size < 32u ? 32u : size & ~31u;
-        base = atomicAdd(&q.count[4], size);
+        base = static_total + atomicAdd(&q.count[4], size);
       }
       base = __shfl_sync(kFull, base, 0);
       size = __shfl_sync(kFull, size, 0);

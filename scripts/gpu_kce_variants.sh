@@ -1,0 +1,9 @@
+set -u
+OUT=gpurun_out/r02r; mkdir -p $OUT
+cp minimc_b200/libminimc_b200.so /tmp/base.so
+for v in base CEB2; do
+  [ $v = base ] || cp minimc_b200/csrc/build/variants/$v.so minimc_b200/libminimc_b200.so
+  python bench.py --workload keigenvalue_ce --steps 6 --warmup 2 2>/dev/null > $OUT/kce_$v.json
+  python -c "import json;j=json.loads(open('$OUT/kce_$v.json').read().strip().splitlines()[-1]);print('$v', '%.4g'%j['value'], j['ms_per_step'])"
+done
+cp /tmp/base.so minimc_b200/libminimc_b200.so
