@@ -168,10 +168,12 @@ ROOFLINE_NOTE = {
     "event": "bytes = 72*births + 144*events + 16*scores + 144*banked (BASELINE.md s4) per step; a 'launch' is the "
              "whole pass loop of one step (flight, boundary and S(a,b) kernel per event, kernel_split has their CUDA-event "
              "times and counts); particle state really streams through HBM here (traffic = ncu DRAM bytes). The "
-             "dominant S(a,b) kernel is not HBM-bound: its first version sat at 88 % of peak L1 wavefronts (per-lane "
-             "table gathers); with the POD factors expanded into dense tables on the device (two adjacent loads per "
-             "reconstruction, L2-resident) it runs 24 warps per SM at 43 % of issue slots, the stalls led by the L2 "
-             "latency of the table gathers: see DESIGN.md s3, s4.1, s7 and profiles/",
+             "dominant S(a,b) kernel is not HBM-bound: every lane gathers from its own table row, so the kernel pays "
+             "for the number of gather instructions (up to 32 L1 wavefronts each). With evaluated tables per constant "
+             "cell temperature a reconstruction is one load; the kernel kind that holds only the direct samplers runs "
+             "32 warps per SM at 64 registers and 54 % of issue slots (ncu, profiles/r02s_*), stalls led by "
+             "long_scoreboard (L1/L2 latency of the gathers) and fixed-latency fp64 chains: see DESIGN.md s3, s4.1, "
+             "s7 and profiles/",
 }
 
 
