@@ -152,6 +152,7 @@ struct mmc_world {
   bool has_fission = false;
   int sm_count = 0;
   size_t smem_optin = 0;
+  size_t l2_persist_bytes = 0;  // persisting-L2 set-aside asked for so far (keep_tables_in_l2)
   cudaStream_t stream = nullptr;
   // scratch reused between runs
   BankSite* d_sites = nullptr;
@@ -516,9 +517,40 @@ int ensure_event_buffers(mmc_world* w, uint32_t n_slots, EventBuffers& out) {
 // The pass loop of the event-split schedule.  One pass = one event of every live history (flight kernel + S(a,b)
 // kernel).  The number of live slots is read back every few passes: it bounds the next launches' grids and ends the
 // loop.  Passes over an empty queue are no-ops, so checking late is harmless.
+// The world's tables (image + dense / evaluated tail, ~10 MB at the reference's shapes) are gathered from by every event
+// while 200 MB of slot state stream through the same L2 twice per pass: an access-policy window marks the tables
+// persisting on the stream the event kernels run on, so the streaming state does not evict them.
+// MMC_L2_PERSIST=0 leaves the stream alone (development A/B).
+void keep_tables_in_l2(mmc_world* w, cudaStream_t stream) {
+  static const bool enabled = !(std::getenv("MMC_L2_PERSIST") && std::atoi(std::getenv("MMC_L2_PERSIST")) == 0);
+  if (!enabled || !stream) return;
+  int max_window = 0, max_persist = 0;
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, w->device);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, w->device);
+  const size_t bytes = static_cast<size_t>(w->blob_bytes) + w->header.dense_bytes;
+  if (max_window <= 0 || max_persist <= 0 || bytes == 0) return;
+  const size_t window = std::min<size_t>(bytes, static_cast<size_t>(max_window));
+  if (w->l2_persist_bytes < window) {
+    const size_t want = std::min<size_t>(std::max<size_t>(window, size_t{16} << 20), static_cast<size_t>(max_persist));
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    w->l2_persist_bytes = window;
+  }
+  cudaStreamAttrValue attr{};
+  attr.accessPolicyWindow.base_ptr = w->d_blob;
+  attr.accessPolicyWindow.num_bytes = window;
+  attr.accessPolicyWindow.hitRatio = 1.0f;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_scores, unsigned long long* d_square,
                        mmc_counters* d_counters) {
   EventBuffers b;
+  keep_tables_in_l2(w, p.stream);
   if (int s = ensure_event_buffers(w, p.event_slots, b)) return s;
   if (int s = ensure_scratch(w, p.event_slots, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
   if (!p.bounds.empty())
