@@ -147,10 +147,9 @@ struct TslPartition {
   // and find_cdf's comparator probes one contiguous row of n_cdf doubles.  0 = none.
   uint32_t off_eval;
   // 1: every evaluated row is non-decreasing in the CDF node (checked on the device after each evaluation,
-  // kernels.cu check_rows_sorted_kernel).  std::upper_bound over such a row gives the same index whatever the probe
-  // sequence, so find_cdf (ThermalScattering.cpp:398-421) may search it with a few rounds of independent loads instead
-  // of libstdc++'s ~log2(n_cdf) dependent probes.  0: keep libstdc++'s probe sequence (the result of a search over a
-  // row that is not sorted depends on it).
+  // kernels.cu check_rows_sorted_kernel).  Kept as the condition for TslTable::direct.  (r02: find_cdf's search,
+  // ce::find_cdf_bisect, now makes libstdc++'s own probes, so its index no longer depends on this; the earlier
+  // search by rounds of independent loads did.  The flag stays conservative rather than being re-argued.)
   uint32_t eval_sorted;
   // double2[n_cdf + 1]: {F_lo, F_hi} of the CDF bracket whose upper index is i -- {cdf[i - 1] or 0, cdf[i] or 1}, the
   // pair ThermalScattering.cpp:313-320,438-447 reads after every search, as one 16-byte load

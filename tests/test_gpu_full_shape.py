@@ -121,9 +121,12 @@ def test_evaluated_tables_change_nothing(full_tables, tmp_path, monkeypatch):
 
 
 def test_sorted_row_search_changes_nothing(full_tables, monkeypatch):
-    """find_cdf over an evaluated, sorted row as rounds of independent loads (physics_ce.cuh find_cdf_sorted,
-    TslPartition::eval_sorted) against libstdc++'s probe sequence (MMC_TSL_SORTED_SEARCH=0): identical tallies, counters
-    and traces on single_zone and multi_zone at full shape, event-split and fused schedule."""
+    """The S(a,b) kernel kind that holds only the direct samplers over evaluated rows (WorldHeader::tsl_all_direct:
+    one load per reconstruction, the CDF lookup table, ce::find_cdf_bisect) against the kind a world falls back to when
+    its tables are not TslTable::direct (MMC_TSL_SORTED_SEARCH=0 clears the flag: the dense kind, direct samplers over
+    two-row reconstructions): identical tallies, counters and traces on single_zone and multi_zone at full shape,
+    event-split and fused schedule.  (Until r02m the default searched sorted rows by rounds of independent loads, which
+    is what the environment variable is named after.)"""
     n = 100_000
     for name in ("single_zone", "multi_zone"):
         text = FULL_DECKS[name](full_tables, histories=n)
