@@ -41,6 +41,12 @@ constexpr uint32_t kDefaultEventSlots = 1u << 20;
 // 1.5 * 2^20 1.407e8, 2^21 1.419e8, 2^22 1.397e8 hist/s): the longer drain tail of more slots is amortised
 constexpr uint32_t kLargeBatchEventSlots = 1u << 21;
 constexpr uint64_t kLargeBatchHistories = 1ull << 24;
+// batches below 3 * 2^20 histories (r02w/r02x, single_zone, ms per step at 2^19 | 2^20 slots: 10^6 histories -- the
+// deck as shipped -- 11.28 | 11.95, 2 * 10^6 16.49 | 17.11, 2^22 28.10 | 27.64, 1.25 * 10^7 72.6 | 67.6; 2^18 and
+// 3/4 * 2^20 at 10^6: 12.00 and 11.48).  Why fewer slots than histories pay there was not established (50 MB of slot
+// state instead of 100 is one candidate); the choice is the measurement's.
+constexpr uint32_t kSmallBatchEventSlots = 1u << 19;
+constexpr uint64_t kSmallBatchHistories = 3ull << 20;
 // live histories at or below which the drain of an event-split run is handed to the fused kernel
 constexpr uint32_t kDefaultEventHandover = 1u << 15;
 
@@ -466,7 +472,9 @@ int prepare_run(
     return fail(MMC_ERR_INVALID, "MMC_SCHEDULE_EVENT is for continuous-energy fixed-source runs");
   out.event_schedule = continuous_energy && !generation && !trace && schedule != MMC_SCHEDULE_FUSED;
   if (out.event_schedule) {
-    if (slots == 0) slots = n_histories >= kLargeBatchHistories ? kLargeBatchEventSlots : kDefaultEventSlots;
+    if (slots == 0)
+      slots = n_histories >= kLargeBatchHistories ? kLargeBatchEventSlots
+              : n_histories < kSmallBatchHistories ? kSmallBatchEventSlots : kDefaultEventSlots;
     // worlds with fission keep a secondary deque per slot: bound its memory
     if (w->has_fission) slots = std::min<uint32_t>(slots, 1u << 18);
     out.event_slots = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(n_histories, 1), slots));
