@@ -259,7 +259,12 @@ typedef struct mmc_run_options {
   uint32_t pending_capacity;        /* per-history distinct scored bins (default 32) */
   uint32_t blocks_per_sm;           /* 0 = library default */
   uint32_t schedule;                /* mmc_schedule; 0 = library default */
-  void* stream;                     /* cudaStream_t; NULL = the library's own stream */
+  void* stream;                     /* cudaStream_t; NULL = the library's own stream.  For the duration of an event-split
+                                     * run the library puts an L2 access-policy window over the world's tables on this
+                                     * stream (and, once per world, raises the device's persisting-L2 set-aside to hold
+                                     * them, cudaLimitPersistingL2CacheSize: a device-wide setting); a caller's stream
+                                     * has its window cleared again before the call returns.  MMC_L2_PERSIST=0 in the
+                                     * environment turns both off. */
   uint32_t event_slots;             /* MMC_SCHEDULE_EVENT: histories in flight at once (0 = library default) */
   uint32_t profile;                 /* MMC_SCHEDULE_EVENT: 1 = time every kernel with CUDA events (mmc_world_last_kernel_ms) */
 } mmc_run_options;

@@ -555,10 +555,17 @@ void keep_tables_in_l2(mmc_world* w, cudaStream_t stream) {
   if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
+// A caller's stream gets its access policy back once the run's launches are enqueued (the window is taken at launch,
+// so the kernels already in the stream keep it); the world's own stream keeps the window between runs.
+void release_l2_window(const mmc_world* w, cudaStream_t stream) {
+  if (!stream || stream == w->stream) return;
+  cudaStreamAttrValue attr{};  // num_bytes = 0: no window
+  if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_scores, unsigned long long* d_square,
                        mmc_counters* d_counters) {
   EventBuffers b;
-  keep_tables_in_l2(w, p.stream);
   if (int s = ensure_event_buffers(w, p.event_slots, b)) return s;
   if (int s = ensure_scratch(w, p.event_slots, p.run.secondary_capacity, p.run.pending_capacity, p.bounds.size())) return s;
   if (!p.bounds.empty())
@@ -569,6 +576,7 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
   MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_event_init, b.st, b.q, p.event_slots, b.counter_replicas, p.stream));
   uint32_t alive = p.event_slots, pass = 0;
   w->last_launches = 1;
+  keep_tables_in_l2(w, p.stream);  // (every exit below this line goes through release_l2_window)
   // profile mode: CUDA events around every kernel of every pass (flight | S(a,b)), summed after the run
   std::vector<cudaEvent_t> marks;
   auto mark = [&]() -> cudaEvent_t {
@@ -628,8 +636,13 @@ int run_event_schedule(mmc_world* w, const Prepared& p, unsigned long long* d_sc
     if (cudaEventElapsedTime(&c, marks[k + 2], marks[k + 3]) == cudaSuccess) w->last_tsl_ms += c;
   }
   for (cudaEvent_t e : marks) cudaEventDestroy(e);
-  if (status != MMC_OK) return status;
-  MMC_CUDA(MMC_BY_RNG(p.counter_rng, launch_event_finish, b.counter_replicas, d_counters, p.stream));
+  if (status != MMC_OK) {
+    release_l2_window(w, p.stream);
+    return status;
+  }
+  const cudaError_t finish = MMC_BY_RNG(p.counter_rng, launch_event_finish, b.counter_replicas, d_counters, p.stream);
+  release_l2_window(w, p.stream);
+  MMC_CUDA(finish);
   w->last_launches += 1;
   return MMC_OK;
 }
