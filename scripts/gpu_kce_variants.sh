@@ -1,3 +1,6 @@
+#!/bin/bash
+# On the GPU box: the CE k-eigenvalue bench with the base library and with the CEB2 variant (fused CE kernels at 2 CTAs
+# per SM, scripts/build_variant.sh CEB2 -DMMC_CE_BLOCKS_PER_SM=2).  r02r: 2.285e7 against 2.048e7 hist/s: 3 CTAs stay.
 set -u
 OUT=gpurun_out/r02r; mkdir -p $OUT
 cp minimc_b200/libminimc_b200.so /tmp/base.so
